@@ -1,0 +1,112 @@
+// Error plumbing and library identity for libattngan_b200 (C ABI in include/attngan_b200.h).
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "agb_common.cuh"
+
+namespace agb {
+
+static thread_local char g_err[512] = "";
+
+static void vset(const char* fmt, va_list ap) { vsnprintf(g_err, sizeof(g_err), fmt, ap); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vset(fmt, ap);
+  va_end(ap);
+}
+int fail_arg(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vset(fmt, ap);
+  va_end(ap);
+  return AGB_E_BADARG;
+}
+int fail_unsupported(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vset(fmt, ap);
+  va_end(ap);
+  return AGB_E_UNSUPPORTED;
+}
+static std::atomic<long long> g_launches{0};
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+
+// ---- optional per-kernel timing (CUDA events on the launching stream) -------------------------
+struct ProfRec {
+  cudaEvent_t a, b;
+  int tag;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;       // pool, reused across enable() calls
+static size_t g_prof_used = 0;
+static bool g_prof_on = false;
+static long long g_prof_dropped = 0;
+
+int prof_begin(int tag, cudaStream_t st) {
+  if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_used == g_prof.size()) {
+    if (g_prof.size() >= 16384) {
+      ++g_prof_dropped;
+      return -1;
+    }
+    ProfRec r;
+    r.tag = tag;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+    g_prof.push_back(r);
+  }
+  const int slot = (int)g_prof_used++;
+  g_prof[slot].tag = tag;
+  cudaEventRecord(g_prof[slot].a, st);
+  return slot;
+}
+void prof_end(int slot, cudaStream_t st) {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, st);
+}
+
+}  // namespace agb
+
+extern "C" void agb_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(agb::g_prof_mu);
+  agb::g_prof_on = on != 0;
+  agb::g_prof_used = 0;
+  agb::g_prof_dropped = 0;
+}
+
+extern "C" int agb_prof_read(int tag, double* total_ms, long long* launches) {
+  std::lock_guard<std::mutex> lk(agb::g_prof_mu);
+  double tot = 0.0;
+  long long n = 0;
+  for (size_t i = 0; i < agb::g_prof_used; ++i) {
+    if (agb::g_prof[i].tag != tag) continue;
+    cudaError_t e = cudaEventSynchronize(agb::g_prof[i].b);
+    if (e != cudaSuccess) return (int)e;
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, agb::g_prof[i].a, agb::g_prof[i].b);
+    if (e != cudaSuccess) return (int)e;
+    tot += ms;
+    ++n;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  return agb::g_prof_dropped ? -3 : 0;
+}
+
+extern "C" long long agb_launch_count(void) { return agb::g_launches.load(); }
+
+extern "C" int agb_version(void) { return AGB_VERSION; }
+extern "C" const char* agb_last_error(void) { return agb::g_err; }

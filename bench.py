@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""Benchmark of the word-region attention hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--workload cfg2|cfg4|cfg3|cfg1] [--math fp32|f16|bf16] [--batch B]
+
+One "step" is one pass of the hot path over one batch of synthetic input:
+  cfg2 (default at N=1)  DAMSM WordsLoss + SentenceLoss forward+backward, batch 48, 17x17 regions,
+                         T=18, D=256 (grads w.r.t. region features, word embeddings, both codes)
+  cfg4 (default at N>1)  the same step at global batch 2048 sharded over the N ranks (word features
+                         all-gathered over NCCL so the negatives span the global batch); strong scaling
+  cfg3 / cfg1            generator word attention forward+backward (bf16 B=64 128x128 / fp32 B=16 64x64)
+Metric: pairs/s (image-caption pairs) for the DAMSM step, pixels/s for the attention workloads.
+
+`value` is measured with inputs resident in HBM; `e2e` through the public drop-in API with pinned
+HOST inputs (host->device copies and the device->host read of the losses inside the timed region).
+`roofline` is for the dominant kernel, timed live with CUDA events on its launching stream
+(agb_prof_* hooks); `cpu_baseline` / `--impl reference` time the oracle port of the reference
+(the reference itself is Python and does not travel to the GPU box) on the host cores.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R_, T_, D_ = 289, 18, 256
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sust=float(p["bf16_tflops_sustained"]), source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_damsm_step(B, seed=0):
+    import torch
+    from oracle import ref_port as rp
+    img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, T=T_, D=D_, hw=17, seed=seed, n_classes=max(2, B // 4))
+    img.requires_grad_(True)
+    wrd = wrd.detach().clone().requires_grad_(True)
+    cnn.requires_grad_(True)
+    rnn.requires_grad_(True)
+
+    def step():
+        for t in (img, wrd, cnn, rnn):
+            t.grad = None
+        wl, _ = rp.words_loss(img, wrd, labels, lens, cls)
+        sl = rp.sentence_loss(cnn, rnn, labels, cls)
+        (wl + sl).backward()
+        return float(wl) + float(sl)
+    return step, B * B
+
+
+def cpu_attn_step(B, C, E, T, hw, seed=0):
+    import torch
+    from oracle import ref_port as rp
+    images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed)
+    images.requires_grad_(True)
+    words = words.detach().clone().requires_grad_(True)
+    weight.requires_grad_(True)
+    dctx = torch.randn(B, C, hw, hw)
+
+    def step():
+        for t in (images, words, weight):
+            t.grad = None
+        ctx, _ = rp.word_attention(images, words, weight, mask)
+        ctx.backward(dctx)
+        return 0.0
+    return step, B * hw * hw
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if args.workload in ("cfg2", "cfg4"):
+        B = 48 if args.workload == "cfg2" else 96
+        step, units = cpu_damsm_step(B)
+        metric, unit = "damsm_words_sentence_loss_fwd_bwd_pairs_per_sec", "pairs/s"
+        sample = (f"oracle/ref_port.py (op-by-op torch-CPU port of the reference) WordsLoss+SentenceLoss fwd+bwd, "
+                  f"B={B} (R=289,T=18,D=256), fp32" + ("" if args.workload == "cfg2" else
+                                                      "; bounded sample of the global-batch-2048 workload"))
+        workload = "cfg2: DAMSM words+sentence loss fwd+bwd, B=48, R=289, T=18, D=256" if args.workload == "cfg2" \
+            else "cfg4: DAMSM step, global batch 2048 (CPU arm: per-pair rate on a B=96 sample)"
+    else:
+        B, C, E, T, hw = (16, 32, 256, 18, 64) if args.workload == "cfg1" else (4, 32, 256, 18, 128)
+        step, units = cpu_attn_step(B, C, E, T, hw)
+        metric, unit = "word_attention_fwd_bwd_pixels_per_sec", "pixels/s"
+        sample = f"oracle/ref_port.py word_attention fwd+bwd fp32, B={B}, {hw}x{hw}, T={T}, C={C}"
+        workload = f"{args.workload}: generator word attention fwd+bwd (CPU arm: B={B}, {hw}x{hw}, fp32)"
+    sec = time_cpu(step, args.steps, args.warmup)
+    v = units / sec
+    line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload},
+            "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def prof_read(lib, tag):
+    ms = ctypes.c_double(0.0)
+    n = ctypes.c_longlong(0)
+    lib.agb_prof_read(tag, ctypes.byref(ms), ctypes.byref(n))
+    return ms.value, n.value
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import attention_gan_b200 as pkg
+    from oracle import ref_port as rp          # seeded input generators only (bench may use oracle/ as a checker)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    lib = pkg.native.lib()
+    peaks = load_peaks()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    damsm = args.workload in ("cfg2", "cfg4")
+    if damsm:
+        Bg = args.batch or (48 if args.workload == "cfg2" else 2048)
+        assert Bg % world == 0
+        Bl = Bg // world
+        # every rank generates the same global batch from one seed and keeps its shard
+        g = torch.Generator().manual_seed(0)
+        sl = slice(rank * Bl, rank * Bl + Bl)
+        img_h = torch.randn(Bg, D_, 17, 17, generator=g)[sl].contiguous().pin_memory()
+        wrd_h = torch.randn(Bg, T_, D_, generator=g)[sl].contiguous().pin_memory()     # physical [B,T,D]
+        cnn_h = torch.randn(Bg, D_, generator=g)[sl].contiguous().pin_memory()
+        rnn_h = torch.randn(Bg, D_, generator=g)[sl].contiguous().pin_memory()
+        lens_h = torch.randint(2, T_ + 1, (Bg,), generator=g, dtype=torch.int64)
+        lens_h[0] = T_
+        mean_len = float(lens_h.float().mean())
+        lens_h = lens_h[sl].contiguous().pin_memory()
+        cls_np = torch.randint(0, 500, (Bg,), generator=g, dtype=torch.int64)[sl].numpy()
+        labels = torch.arange(Bl, device=dev)
+        loss_mod = pkg.DAMSMLoss(dev, math=args.math, process_group=group, att_maps="packed")
+        out_h = torch.empty(2, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in (img_h, wrd_h, cnn_h, rnn_h, lens_h)) + cls_np.nbytes
+        d2h = 8
+
+        def make_dev():
+            ts = [img_h.to(dev), wrd_h.to(dev), cnn_h.to(dev), rnn_h.to(dev)]
+            for t in ts:
+                t.requires_grad_(True)
+            return ts + [lens_h.to(dev), torch.from_numpy(cls_np).to(dev, torch.int32)]
+
+        def step_dev(ts):
+            img, wrd, cnn, rnn, lens, cls = ts
+            for t in (img, wrd, cnn, rnn):
+                t.grad = None
+            wl, sls, _ = loss_mod.get_losses(img, cnn, wrd.transpose(1, 2), rnn, labels, lens, cls)
+            (wl + sls).backward()
+            return wl, sls
+
+        def step_e2e():
+            ts = [img_h.to(dev, non_blocking=True).requires_grad_(True),
+                  wrd_h.to(dev, non_blocking=True).requires_grad_(True),
+                  cnn_h.to(dev, non_blocking=True).requires_grad_(True),
+                  rnn_h.to(dev, non_blocking=True).requires_grad_(True),
+                  lens_h.to(dev, non_blocking=True)]
+            img, wrd, cnn, rnn, lens = ts
+            wl, sls, _ = loss_mod.get_losses(img, cnn, wrd.transpose(1, 2), rnn, labels, lens, cls_np)
+            (wl + sls).backward()
+            out_h[0:1].copy_(wl.detach().reshape(1), non_blocking=True)
+            out_h[1:2].copy_(sls.detach().reshape(1), non_blocking=True)
+
+        units = Bl * Bg                       # pairs this rank computes per step
+        total_units = Bg * Bg
+        metric, unit = "damsm_words_sentence_loss_fwd_bwd_pairs_per_sec", "pairs/s"
+        workload = (f"{args.workload}: DAMSM WordsLoss+SentenceLoss fwd+bwd, global batch {Bg}"
+                    f"{' sharded over %d ranks' % world if world > 1 else ''}, R=289, T=18 (cap_lens U{{2..18}}), D=256, "
+                    f"class_ids U{{0..499}}, math={args.math}")
+        flop_per_unit = 12.0 * R_ * mean_len * D_
+        tc = args.math != "fp32"
+        tags = [2, 3] if tc else [1]
+        dtype = {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.math]
+    else:
+        if args.workload == "cfg1":
+            B, C, E, T, hw, tdt = 16, 32, 256, 18, 64, torch.float32
+        else:
+            B, C, E, T, hw, tdt = 64, 32, 256, 18, 128, torch.bfloat16
+        B = args.batch or B
+        assert B % world == 0
+        Bl = B // world
+        images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed=0)
+        sl = slice(rank * Bl, rank * Bl + Bl)
+        g = torch.Generator().manual_seed(1)
+        img_h = images[sl].to(tdt).contiguous().pin_memory()
+        dctx_h = torch.randn(B, C, hw, hw, generator=g)[sl].to(tdt).contiguous().pin_memory()
+        wrd_h = words[sl].transpose(1, 2).contiguous().pin_memory()        # physical [B,T,E]
+        mask_d = mask[sl].to(dev)
+        mod = pkg.AttentionModule(C, E).to(dev)
+        with torch.no_grad():
+            mod.conv1.weight.copy_(weight.to(dev))
+        mod.apply_mask(mask_d)
+        out_h = torch.empty(1, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in (img_h, dctx_h, wrd_h))
+        d2h = 4
+
+        def make_dev():
+            return [img_h.to(dev).requires_grad_(True), wrd_h.to(dev).requires_grad_(True), dctx_h.to(dev)]
+
+        def step_dev(ts):
+            im, wd, dctx = ts
+            im.grad = None
+            wd.grad = None
+            mod.conv1.weight.grad = None
+            ctx, attn = mod(im, wd.transpose(1, 2))
+            ctx.backward(dctx)
+            return ctx, attn
+
+        def step_e2e():
+            im = img_h.to(dev, non_blocking=True).requires_grad_(True)
+            wd = wrd_h.to(dev, non_blocking=True).requires_grad_(True)
+            dctx = dctx_h.to(dev, non_blocking=True)
+            mod.conv1.weight.grad = None
+            ctx, attn = mod(im, wd.transpose(1, 2))
+            ctx.backward(dctx)
+            out_h.copy_(im.grad.float().abs().max().reshape(1), non_blocking=True)   # the step's metric
+
+        units = Bl * hw * hw
+        total_units = B * hw * hw
+        es = 4 if tdt == torch.float32 else 2
+        metric, unit = "word_attention_fwd_bwd_pixels_per_sec", "pixels/s"
+        workload = (f"{args.workload}: AttentionModule fwd+bwd, batch {B}, {hw}x{hw} feature map, T={T}, C={C}, E={E}, "
+                    f"{'fp32' if es == 4 else 'bf16'} I/O")
+        bytes_fwd, bytes_bwd = es * (2 * C + T), es * 3 * C
+        tags = [4, 5]
+        dtype = "f32"          # arithmetic is fp32 in registers; I/O dtype is in config
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    ts = make_dev()
+    for _ in range(args.warmup):
+        step_dev(ts)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lib.agb_prof_enable(1)
+    n0 = lib.agb_launch_count()
+    barrier()
+    for a, b in ev:
+        flush.zero_()                         # L2 flush between timed iterations (outside the events)
+        a.record()
+        step_dev(ts)
+        b.record()
+    barrier()
+    launches = lib.agb_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = {t: prof_read(lib, t) for t in tags}
+    lib.agb_prof_enable(0)
+    sec = sum(a.elapsed_time(b) for a, b in ev) / 1e3 / args.steps
+    tsec = torch.tensor([sec], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+    sec = float(tsec.item())
+
+    # ---- end to end through the public API with host buffers -----------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        step_e2e()
+        b.record()
+    barrier()
+    sec2 = sum(a.elapsed_time(b) for a, b in ev2) / 1e3 / args.steps
+    tsec2 = torch.tensor([sec2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tsec2, op=dist.ReduceOp.MAX)
+    sec2 = float(tsec2.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    if damsm:
+        ms_tot = sum(prof[t][0] for t in tags)
+        n_l = sum(prof[t][1] for t in tags)
+        flops = flop_per_unit * units * args.steps            # algorithmic flops the launches covered
+        ach = flops / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
+        peak = peaks["tf_burst"]
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "kernel": "damsm_tc_fwd/bwd (tcgen05)" if tc else "sgemm_strided_kernel (fp32 CUDA cores)",
+                "launches": int(n_l), "avg_launch_ms": ms_tot / max(n_l, 1),
+                "peak_source": f"{peaks['source']} bf16 burst (kernels timed one by one with events)",
+                "algorithmic": "12*R*mean(cap_len)*D flop per (image,caption) pair, fwd+bwd"}
+    else:
+        (ms_f, n_f), (ms_b, n_b) = prof[4], prof[5]
+        gb = (bytes_fwd + bytes_bwd) * units * args.steps / 1e9
+        ach = gb / ((ms_f + ms_b) * 1e-3) if ms_f + ms_b > 0 else 0.0
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                "traffic": None, "kernel": "word_attn_fwd_kernel + word_attn_bwd_kernel",
+                "launches": int(n_f + n_b), "avg_launch_ms": (ms_f + ms_b) / max(n_f + n_b, 1),
+                "fwd_gbs": bytes_fwd * units * args.steps / 1e9 / (ms_f * 1e-3) if ms_f > 0 else None,
+                "bwd_gbs": bytes_bwd * units * args.steps / 1e9 / (ms_b * 1e-3) if ms_b > 0 else None,
+                "peak_source": f"{peaks['source']} HBM copy",
+                "algorithmic": "es*(2C+T) B/pixel fwd + es*3C B/pixel bwd"}
+
+    # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) -----------------
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if damsm:
+        cstep, cunits = cpu_damsm_step(48)
+        csample = "oracle/ref_port.py WordsLoss+SentenceLoss fwd+bwd at B=48 (cfg2 shape), fp32, 3 steps after 1 warm-up"
+    else:
+        cstep, cunits = cpu_attn_step(16, 32, 256, 18, 64)
+        csample = "oracle/ref_port.py word_attention fwd+bwd at B=16, 64x64 (cfg1 shape), fp32, 3 steps after 1 warm-up"
+    csec = time_cpu(cstep, 3, 1)
+    cpu = {"value": cunits / csec, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": csample}
+
+    line = {"metric": metric, "value": total_units / sec, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic",
+            "config": {"workload": workload, "l2": "256 MiB L2 flush between timed iterations",
+                       "timing": "CUDA events per step on the current stream, max over ranks"},
+            "e2e": {"value": total_units / sec2, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                    "ms_per_step": sec2 * 1e3},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--math", default=None, choices=["fp32", "f16", "bf16"])
+    ap.add_argument("--batch", type=int, default=None)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "cfg2" if max(world, args.gpus) == 1 else "cfg4"
+    if args.impl == "reference":
+        args.warmup = min(args.warmup, 2)    # each CPU step is a bounded sample (0.5-3 s); warm-up is cheap to cap
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    if args.math is None:
+        import attention_gan_b200 as pkg
+        args.math = "f16" if pkg.native.lib().agb_has_tcgen05() else "fp32"
+    run_native(args)
+
+
+if __name__ == "__main__":
+    main()

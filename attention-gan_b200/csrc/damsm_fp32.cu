@@ -100,8 +100,8 @@ __device__ __forceinline__ void block_sum_words(const float (&v)[TMAX], int L, f
 //   att_out [Bi,T,R]: beta of the matched pair (words_loss.py:63); row_offset < 0: every block
 //   cap_lens == nullptr: every caption has T words (func_attention)
 // ---------------------------------------------------------------------------------------------
-template <int TMAX>
-__global__ void pair_softmax_kernel(const float* __restrict__ S, float* __restrict__ Bt,
+template <int TMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT) pair_softmax_kernel(const float* __restrict__ S, float* __restrict__ Bt,
                                     const int32_t* __restrict__ cap_lens, int i0, int N, int T, int R,
                                     float inv_sqrt_d, float gamma1, int row_offset,
                                     float* __restrict__ att_out) {
@@ -230,8 +230,8 @@ pair_cosine_kernel(float* __restrict__ V, const float* __restrict__ Wp, const fl
 //   out: S <- ds / sqrt(D)                      (operand of the dC GEMM)
 //        G <- dn * beta + ds / sqrt(D)          (operand of the dW GEMM)
 // ---------------------------------------------------------------------------------------------
-template <int TMAX>
-__global__ void pair_softmax_bwd_kernel(float* __restrict__ S, const float* __restrict__ Bt,
+template <int TMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT) pair_softmax_bwd_kernel(float* __restrict__ S, const float* __restrict__ Bt,
                                         float* __restrict__ G, const float* __restrict__ stat,
                                         const int32_t* __restrict__ cap_lens, int i0, int N, int T,
                                         int R, float inv_sqrt_d, float gamma1) {
@@ -341,8 +341,12 @@ static int chunk_forward(const float* img, const Fp32Plan& p, char* ws, const in
   if (int rc = sgemm_strided(g, Bi, st)) return rc;
   const int threads = (R + 31) / 32 * 32;
   const int tm = pick_tmax(T);
-  AGB_TMAX_SWITCH(tm, (pair_softmax_kernel<TMAX><<<dim3(nc, Bi), threads, 0, st>>>(
-                          S, Bt, cap_lens, i0, N, T, R, 1.f / sqrtf((float)D), gamma1, row_offset, att_out)));
+  AGB_TMAX_SWITCH(tm, {
+    if (threads <= 352) pair_softmax_kernel<TMAX, 352><<<dim3(nc, Bi), threads, 0, st>>>(
+        S, Bt, cap_lens, i0, N, T, R, 1.f / sqrtf((float)D), gamma1, row_offset, att_out);
+    else pair_softmax_kernel<TMAX, 1024><<<dim3(nc, Bi), threads, 0, st>>>(
+        S, Bt, cap_lens, i0, N, T, R, 1.f / sqrtf((float)D), gamma1, row_offset, att_out);
+  });
   if (int rc = check_launch("pair_softmax_kernel")) return rc;
   // V[b][n,d] = sum_r Bt[b][n,r] * img[b][d,r]                                    attention.py:119
   g.A = Bt; g.a_m = R; g.a_k = 1; g.a_batch = (int64_t)N * R;
@@ -423,8 +427,12 @@ int damsm_fp32_bwd(const float* img, const float* words, int64_t ws_b, int64_t w
     g.C = G; g.c_m = R; g.c_n = 1; g.c_batch = (int64_t)N * R;
     g.M = N; g.N = R; g.K = D; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
     if (int rc = sgemm_strided(g, Bi, st)) return rc;
-    AGB_TMAX_SWITCH(tm, (pair_softmax_bwd_kernel<TMAX><<<dim3(nc, Bi), threads, 0, st>>>(
-                            S, Bt, G, stat, cap_lens, i0, N, T, R, isd, gamma1)));
+    AGB_TMAX_SWITCH(tm, {
+      if (threads <= 352) pair_softmax_bwd_kernel<TMAX, 352><<<dim3(nc, Bi), threads, 0, st>>>(
+          S, Bt, G, stat, cap_lens, i0, N, T, R, isd, gamma1);
+      else pair_softmax_bwd_kernel<TMAX, 1024><<<dim3(nc, Bi), threads, 0, st>>>(
+          S, Bt, G, stat, cap_lens, i0, N, T, R, isd, gamma1);
+    });
     if (int rc = check_launch("pair_softmax_bwd_kernel")) return rc;
     // dimg[b][d,r] (+)= sum_n dV[b][n,d] beta[b][n,r] + sum_n Wp[n,d] ds[b][n,r]/sqrt(D)
     g.A = V; g.a_m = 1; g.a_k = D; g.a_batch = (int64_t)N * D;
@@ -460,8 +468,8 @@ namespace agb {
 
 // backward of both softmaxes when the upstream gradient is arbitrary (dwc and optionally dattn):
 //   G = dbeta (+ dattn);  kappa_t = sum_r beta dbeta (block reduction);  out: S <- ds (scaled)
-template <int TMAX>
-__global__ void func_softmax_bwd_kernel(float* __restrict__ S, const float* __restrict__ Bt,
+template <int TMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT) func_softmax_bwd_kernel(float* __restrict__ S, const float* __restrict__ Bt,
                                         const float* __restrict__ G, const float* __restrict__ dattn,
                                         int T, int R, float scale, float gamma1) {
   __shared__ float red_s[32 * TMAX];
@@ -524,8 +532,12 @@ static int func_scores(const float* query, int64_t qs_b, int64_t qs_d, int64_t q
   g.M = L; g.N = R; g.K = D; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
   if (int rc = sgemm_strided(g, B, st)) return rc;
   const int threads = (R + 31) / 32 * 32;
-  AGB_TMAX_SWITCH(pick_tmax(L), (pair_softmax_kernel<TMAX><<<dim3(1, B), threads, 0, st>>>(
-                                    S, Bt, nullptr, 0, L, L, R, scale, gamma1, -1, attn_out)));
+  AGB_TMAX_SWITCH(pick_tmax(L), {
+    if (threads <= 352) pair_softmax_kernel<TMAX, 352><<<dim3(1, B), threads, 0, st>>>(
+        S, Bt, nullptr, 0, L, L, R, scale, gamma1, -1, attn_out);
+    else pair_softmax_kernel<TMAX, 1024><<<dim3(1, B), threads, 0, st>>>(
+        S, Bt, nullptr, 0, L, L, R, scale, gamma1, -1, attn_out);
+  });
   return check_launch("pair_softmax_kernel");
 }
 
@@ -589,7 +601,10 @@ extern "C" int agb_func_attention_bwd(const float* query, int64_t qs_b, int64_t 
   g.M = L; g.N = R; g.K = D; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
   if (int rc = sgemm_strided(g, B, st)) return rc;
   const int threads = (R + 31) / 32 * 32;
-  AGB_TMAX_SWITCH(pick_tmax(L), (func_softmax_bwd_kernel<TMAX><<<B, threads, 0, st>>>(S, Bt, G, dattn, L, R, scale, gamma1)));
+  AGB_TMAX_SWITCH(pick_tmax(L), {
+    if (threads <= 352) func_softmax_bwd_kernel<TMAX, 352><<<B, threads, 0, st>>>(S, Bt, G, dattn, L, R, scale, gamma1);
+    else func_softmax_bwd_kernel<TMAX, 1024><<<B, threads, 0, st>>>(S, Bt, G, dattn, L, R, scale, gamma1);
+  });
   if (int rc = check_launch("func_softmax_bwd_kernel")) return rc;
   if (dquery) {  // dquery[b][d,t] = sum_r context[b][d,r] ds[b][t,r]
     g.A = context; g.a_m = R; g.a_k = 1; g.a_batch = (int64_t)D * R;

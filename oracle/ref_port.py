@@ -220,7 +220,7 @@ def synth_attention(B: int, C: int = 32, E: int = 256, T: int = 18, hw: int = 64
     words = torch.randn(B, T, E, generator=g, dtype=torch.float32)
     bound = 1.0 / math.sqrt(E)
     weight = (torch.rand(C, E, 1, 1, generator=g, dtype=torch.float32) * 2 - 1) * bound
-    lens = torch.randint(2, T + 1, (B,), generator=g, dtype=torch.int64)
+    lens = torch.randint(min(2, T), T + 1, (B,), generator=g, dtype=torch.int64)
     lens[0] = T
     mask = (torch.arange(T)[None, :] < lens[:, None]).to(torch.int64)
     return images.to(dtype), words.to(dtype).transpose(1, 2), weight.to(dtype), mask, lens

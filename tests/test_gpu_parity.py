@@ -4,7 +4,7 @@ the golden vectors recorded from the unmodified reference and against the oracle
 Tolerances (BASELINE.json north_star): attention maps / contexts 1e-5 relative in fp32, 1e-3 in
 reduced precision; loss values 1e-4 relative.  "Relative" is measured against the tensor's scale
 (max |ref|) for tensors and against |ref| for scalars.  For bf16 storage the final store alone
-rounds by up to 2^-9 relative, so bf16 I/O is checked as: fp32-internal result within 1e-3, i.e.
+rounds by up to 2^-8 relative (8 significand bits), so bf16 I/O is checked as: fp32-internal result within 1e-3, i.e.
 output within 1e-3 + one bf16 rounding of the reference.
 """
 import numpy as np
@@ -93,7 +93,7 @@ def test_attention_module_without_dattn_and_frozen_words(agb):
     assert_rel(mod.conv1.weight.grad, dW.reshape(C, E, 1, 1), 2e-5, "dweight")
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-3 + 2.0 ** -9), (torch.float16, 1e-3)])
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 1e-3 + 2.0 ** -8), (torch.float16, 1e-3)])
 def test_attention_module_reduced_precision_io(agb, dtype, tol):
     B, C, E, T, hw = 4, 32, 256, 18, 32
     images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed=21)

@@ -56,6 +56,13 @@ int agb_has_tcgen05(void);
  * tag: 1 = fp32 sgemm, 2 = tcgen05 DAMSM forward, 3 = tcgen05 DAMSM backward,
  *      4 = word-attention forward, 5 = word-attention backward (main kernel).
  * agb_prof_read synchronises the recorded events and returns the summed duration and the count. */
+/* Self-test of the tcgen05 / TMEM / TMA building blocks: one CTA computes
+ * C[128,N] = A[128,K] * B[N,K]^T from 16-bit row-major device buffers (fp32 accumulate in TMEM).
+ * K % 64 == 0, K <= 256, N in {128, 256}; manual_a != 0 stages A through the thread-written
+ * swizzled shared-memory path instead of TMA. */
+int agb_tc_selftest(const void* A, const void* B, float* C, int N, int K, int bf16, int manual_a,
+                    void* stream);
+
 long long agb_launch_count(void);
 void agb_prof_enable(int on);
 int agb_prof_read(int tag, double* total_ms, long long* launches);

@@ -20,7 +20,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libattngan_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math", ]
+         "-Xcompiler", "-fPIC", "--use_fast_math", "-DAGB_WITH_TC"]
 # --use_fast_math only affects intrinsics we already call explicitly (__expf) plus division /
 # sqrt rounding; the parity tests bound its effect.
 

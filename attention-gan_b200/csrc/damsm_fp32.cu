@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(MAXT) pair_softmax_kernel(const float* __restr
   __shared__ float red_s[32 * TMAX];
   __shared__ float z_s[TMAX];
   const int ic = blockIdx.x, b = blockIdx.y, r = threadIdx.x;
-  const int i = i0 + ic;
+  // i0 < 0: "matched pairs" mode, block b pairs image b with caption row_offset + b
+  const int i = i0 < 0 ? row_offset + b : i0 + ic;
   const int L = cap_lens ? min(max(cap_lens[i], 0), T) : T;
   const bool live = r < R;
   const size_t base = ((size_t)b * N + (size_t)ic * T) * R + r;
@@ -539,6 +540,28 @@ static int func_scores(const float* query, int64_t qs_b, int64_t qs_d, int64_t q
         S, Bt, nullptr, 0, L, L, R, scale, gamma1, -1, attn_out);
   });
   return check_launch("pair_softmax_kernel");
+}
+
+// beta of the matched pairs only (image b, caption row_offset + b), fp32: the att_maps output of
+// WordsLoss (words_loss.py:63) for the tensor-core path.  S, Bt: scratch [Bi,T,R] each.
+int damsm_diag_att_maps(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                        const int32_t* cap_lens, int Bi, int T, int D, int R, float gamma1, int row_offset,
+                        float* att_out, float* S, float* Bt, cudaStream_t st) {
+  SgemmArgs g{};
+  g.A = words + (int64_t)row_offset * ws_b; g.a_m = ws_t; g.a_k = ws_d; g.a_batch = ws_b;
+  g.B = img; g.b_k = R; g.b_n = 1; g.b_batch = (int64_t)D * R;
+  g.C = S; g.c_m = R; g.c_n = 1; g.c_batch = (int64_t)T * R;
+  g.M = T; g.N = R; g.K = D; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
+  if (int rc = sgemm_strided(g, Bi, st)) return rc;
+  const int threads = (R + 31) / 32 * 32;
+  const float isd = 1.f / sqrtf((float)D);
+  AGB_TMAX_SWITCH(pick_tmax(T), {
+    if (threads <= 352) pair_softmax_kernel<TMAX, 352><<<dim3(1, Bi), threads, 0, st>>>(
+        S, Bt, cap_lens, -1, T, T, R, isd, gamma1, row_offset, att_out);
+    else pair_softmax_kernel<TMAX, 1024><<<dim3(1, Bi), threads, 0, st>>>(
+        S, Bt, cap_lens, -1, T, T, R, isd, gamma1, row_offset, att_out);
+  });
+  return check_launch("pair_softmax_kernel(diag)");
 }
 
 }  // namespace agb

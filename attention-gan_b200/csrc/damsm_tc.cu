@@ -1,0 +1,546 @@
+// DAMSM word-region similarity on the 5th-generation tensor cores (AGB_MATH_TC_F16 / _BF16).
+//
+// Replaces the loop body of WordsLoss.get_loss (reference losses/words_loss.py:43-86) and the
+// func_attention it calls (networks/attention.py:82-121) with ONE persistent kernel:
+//
+//   work item  = (image b, word tile c): up to 128 caption words (whole captions, packed by
+//                their real lengths, so padded words cost nothing)
+//   GEMM1      S[r, n]  = sum_d C_b[d, r] W[n, d]          3 M-tiles of 128 regions, N = 128, K = 256
+//   epilogue 1 alpha = softmax over the words of each caption (thread = region: thread-local),
+//              e = exp(gamma1 * alpha)  -> 16-bit, written K-major / 128B-swizzled to shared memory
+//   GEMM2      V[n, d]  = sum_r e[r, n] C_b[d, r]          M = 128 words, N = 256, K = 320
+//   epilogue 2 cos_n = <w_n, V_n> / (|w_n| |V_n|)   (thread = word: thread-local; the region-softmax
+//              normaliser cancels in the cosine), m[b, i] = log sum_t exp(gamma2 cos)
+//
+// Operands reach the tensor core by TMA (128B swizzle, K-major); accumulators live in TMEM:
+// columns [0,256) = two S buffers (MMA of M-tile j+1 overlaps epilogue 1 of M-tile j),
+// columns [256,512) = V.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
+// 4..15 = three epilogue warpgroups (one per M-tile).
+//
+// HBM layout of the pre-packed operands (written by the pack kernels below, 16-bit):
+//   Wh [tiles*128, 256]   packed caption words, K-major rows; unused rows are zero
+//   Ct [Bi*384, 256]      regions as rows (M operand of GEMM1), rows >= R zero
+//   Ck [Bi*256, 320]      features as rows (N operand of GEMM2), columns >= R zero
+#include <algorithm>
+#include <type_traits>
+
+#include "tc_common.cuh"
+
+namespace agb {
+
+int sent_cos_fwd_launch(const float* cnn, const float* rnn, int Bi, int Bc, int D, float eps, float* scos_out,
+                        cudaStream_t st);
+int damsm_diag_att_maps(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                        const int32_t* cap_lens, int Bi, int T, int D, int R, float gamma1, int row_offset,
+                        float* att_out, float* S, float* Bt, cudaStream_t st);
+size_t damsm_fp32_workspace_bytes(int Bi, int Bc, int T, int D, int R);
+int damsm_fp32_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                   const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
+                   float eps, const float* dm, const float* gscale, float* dimg, float* dwords, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st);
+
+namespace tc {
+
+constexpr int kD = 256;                   // feature dim: K of GEMM1, N of GEMM2
+constexpr int kTileN = 128;               // word rows per tile
+constexpr int kRRows = 384;               // region rows per image in Ct (3 M-tiles)
+constexpr int kRCols = 320;               // region columns per image in Ck / e (5 chunks of 64)
+constexpr int kChunk = 128 * 128;         // one [128 x 64] 16-bit K-major tile: 16 KB
+constexpr int kSlot = 2 * kChunk;         // ring slot: 32 KB
+constexpr int kThreads = 512;
+constexpr int kSmemW = 0;                 // [4][128 x 64]  resident word tile       64 KB
+constexpr int kSmemE = 4 * kChunk;        // [5][128 x 64]  e = exp(gamma1 alpha)    80 KB
+constexpr int kSmemRing = 9 * kChunk;     // 2 slots                                  64 KB
+constexpr int kSmemBytes = 13 * kChunk + 1024;
+
+template <typename T16> __device__ __forceinline__ T16 cvt16(float v);
+template <> __device__ __forceinline__ __half cvt16<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T16> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack kernels
+// ---------------------------------------------------------------------------------------------
+// greedy packing of whole captions into tiles of <= 128 word rows (and <= 128 captions)
+__global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, int T, int32_t* __restrict__ cap_row,
+                                 int32_t* __restrict__ tile_first, int32_t* __restrict__ tile_ncap,
+                                 int32_t* __restrict__ ntiles) {
+  __shared__ int lens_s[1024];
+  int row = 0, tile = 0, first = 0;
+  for (int base = 0; base < Bc; base += 1024) {
+    const int n = min(1024, Bc - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) lens_s[i] = min(max(cap_lens[base + i], 0), T);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < n; ++k) {
+        const int i = base + k, L = lens_s[k];
+        if (row + L > kTileN || i - first == 128) {
+          tile_first[tile] = first;
+          tile_ncap[tile] = i - first;
+          ++tile;
+          first = i;
+          row = 0;
+        }
+        cap_row[i] = tile * kTileN + row;
+        row += L;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    tile_first[tile] = first;
+    tile_ncap[tile] = Bc - first;
+    ntiles[0] = tile + 1;
+  }
+}
+
+template <typename T16>
+__global__ void pack_words_kernel_tc(const float* __restrict__ words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                                     const int32_t* __restrict__ cap_lens, const int32_t* __restrict__ cap_row,
+                                     T16* __restrict__ Wh, float* __restrict__ pn, int T) {
+  const int i = blockIdx.x, t = blockIdx.y;
+  const int L = min(max(cap_lens[i], 0), T);
+  if (t >= L) return;
+  const size_t row = (size_t)cap_row[i] + t;
+  const float* src = words + (int64_t)i * ws_b + (int64_t)t * ws_t;
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < kD; d += blockDim.x) {
+    const float v = src[(int64_t)d * ws_d];
+    Wh[row * kD + d] = cvt16<T16>(v);
+    ss = fmaf(v, v, ss);
+  }
+  __shared__ float red[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    pn[row] = sqrtf(tot);
+  }
+}
+
+// img [Bi,256,R] fp32 -> Ck [Bi*256, 320] (same orientation, padded) and Ct [Bi*384, 256] (transposed)
+template <typename T16>
+__global__ void pack_img_kernel_tc(const float* __restrict__ img, T16* __restrict__ Ck, T16* __restrict__ Ct, int R) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, d0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // r0 < 384
+  const int tx = threadIdx.x, ty = threadIdx.y;                            // 32 x 8
+  for (int k = ty; k < 32; k += 8) {
+    const int d = d0 + k, r = r0 + tx;
+    const float v = (r < R) ? img[((size_t)b * kD + d) * R + r] : 0.f;
+    tile[k][tx] = v;
+    if (r < kRCols) Ck[((size_t)b * kD + d) * kRCols + r] = cvt16<T16>(v);
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int r = r0 + k, d = d0 + tx;
+    Ct[((size_t)b * kRRows + r) * kD + d] = cvt16<T16>(tile[tx][k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue 1 for one caption: NL = caption length rounded up to a multiple of 8
+// ---------------------------------------------------------------------------------------------
+template <typename T16, int NL>
+__device__ __forceinline__ void caption_softmax(uint32_t taddr, int L, int off, int r, int R, unsigned char* sE,
+                                                float scale_log2, float g1_log2) {
+  float s[NL];
+  if constexpr (NL == 8) tmem_ld8(taddr, s);
+  else if constexpr (NL == 16) tmem_ld16(taddr, s);
+  else if constexpr (NL == 24) { tmem_ld16(taddr, s); tmem_ld8(taddr + 16, s + 16); }
+  else tmem_ld32(taddr, s);
+  tmem_ld_wait();
+  if (r >= kRCols) return;
+  unsigned char* col = sE + (size_t)(r >> 6) * kChunk;
+  const int rc = r & 63;
+  if (r >= R) {  // padding regions contribute nothing to V
+#pragma unroll
+    for (int t = 0; t < NL; ++t)
+      if (t < L) *reinterpret_cast<T16*>(col + sw128_off(off + t, rc)) = cvt16<T16>(0.f);
+    return;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < NL; ++t)
+    if (t < L) mx = fmaxf(mx, s[t]);
+  float sum = 0.f;
+  const float mxs = mx * scale_log2;
+#pragma unroll
+  for (int t = 0; t < NL; ++t)
+    if (t < L) {
+      s[t] = exp2f(fmaf(s[t], scale_log2, -mxs));  // exp((s - max)/sqrt(D))
+      sum += s[t];
+    }
+  const float k = g1_log2 / sum;
+#pragma unroll
+  for (int t = 0; t < NL; ++t)
+    if (t < L) *reinterpret_cast<T16*>(col + sw128_off(off + t, rc)) = cvt16<T16>(exp2f(s[t] * k));  // exp(gamma1 alpha)
+}
+
+struct FwdParams {
+  const int32_t* tile_first;
+  const int32_t* tile_ncap;
+  const int32_t* ntiles;
+  const int32_t* cap_row;
+  const int32_t* cap_lens;
+  const float* pn;
+  float* m_out;
+  int Bi, Bc, T, R;
+  float scale_log2, g1_log2, gamma2;
+};
+
+template <typename T16>
+__global__ void __launch_bounds__(kThreads, 1)
+damsm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapCt,
+                 const __grid_constant__ CUtensorMap mapCk, const FwdParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  unsigned char* sW = smem + kSmemW;
+  unsigned char* sE = smem + kSmemE;
+  unsigned char* sRing = smem + kSmemRing;
+  __shared__ uint64_t w_full, w_empty, slot_full[2], slot_empty[2], s_full[3], s_empty[2], e_ready, v_full, v_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int cap_off_s[128], cap_len_s[128];
+  __shared__ float2 part_s[3][128];
+  __shared__ float cos_s[128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nct = p.ntiles[0];
+  const int total = p.Bi * nct;
+  const int NMT = (p.R + 127) >> 7;
+  const int RKC = (p.R + 63) >> 6;
+  const int last_ks = ((p.R - (RKC - 1) * 64) + 15) >> 4;
+  constexpr int fmt = sizeof(T16) == 2 && std::is_same<T16, __nv_bfloat16>::value ? 1 : 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&w_full, 1);
+    mbar_init(&w_empty, 12);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&slot_full[i], 1);
+      mbar_init(&slot_empty[i], 1);
+      mbar_init(&s_empty[i], 4);
+    }
+    // one "scores ready" barrier per M-tile (one phase per work item): a parity wait is only safe
+    // when the waiter is at most one phase ahead, which a per-buffer barrier would not guarantee
+    for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
+    mbar_init(&e_ready, 12);
+    mbar_init(&v_full, 1);
+    mbar_init(&v_empty, 12);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapW);
+    prefetch_tmap(&mapCt);
+    prefetch_tmap(&mapCk);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t slot_it = 0;
+      int tile_it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tile_it) {
+        const int b = tile / nct, c = tile - b * nct;
+        mbar_wait(&w_empty, (tile_it & 1) ^ 1);
+        mbar_expect_tx(&w_full, 4 * kChunk);
+        for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * kChunk, &mapW, &w_full, kc * 64, c * kTileN);
+        for (int j = 0; j < NMT; ++j)
+          for (int h = 0; h < 2; ++h, ++slot_it) {
+            const int s = slot_it & 1;
+            mbar_wait(&slot_empty[s], ((slot_it >> 1) & 1) ^ 1);
+            mbar_expect_tx(&slot_full[s], kSlot);
+            for (int q = 0; q < 2; ++q)
+              tma_load_2d(sRing + s * kSlot + q * kChunk, &mapCt, &slot_full[s], (2 * h + q) * 64, b * kRRows + j * 128);
+          }
+        for (int rc = 0; rc < RKC; ++rc, ++slot_it) {
+          const int s = slot_it & 1;
+          mbar_wait(&slot_empty[s], ((slot_it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&slot_full[s], kSlot);
+          tma_load_2d(sRing + s * kSlot, &mapCk, &slot_full[s], rc * 64, b * kD);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc1 = make_idesc(128, 128, fmt);
+      constexpr uint32_t idesc2 = make_idesc(128, 256, fmt);
+      uint32_t slot_it = 0, sbuf_it = 0;
+      int tile_it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tile_it) {
+        mbar_wait(&w_full, tile_it & 1);
+        tc_fence_after();
+        for (int j = 0; j < NMT; ++j, ++sbuf_it) {
+          const int buf = sbuf_it & 1;
+          mbar_wait(&s_empty[buf], ((sbuf_it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int h = 0; h < 2; ++h, ++slot_it) {
+            const int s = slot_it & 1;
+            mbar_wait(&slot_full[s], (slot_it >> 1) & 1);
+            tc_fence_after();
+            for (int q = 0; q < 2; ++q) {
+              const uint64_t da = make_desc_sw128(smem_u32(sRing + s * kSlot + q * kChunk));
+              const uint64_t db = make_desc_sw128(smem_u32(sW + (2 * h + q) * kChunk));
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(tmem + buf * 128, da + 2 * kk, db + 2 * kk, idesc1, (h | q | kk) ? 1u : 0u);
+            }
+            umma_commit(&slot_empty[s]);
+          }
+          umma_commit(&s_full[j]);
+        }
+        mbar_wait(&e_ready, tile_it & 1);
+        mbar_wait(&v_empty, (tile_it & 1) ^ 1);
+        tc_fence_after();
+        for (int rc = 0; rc < RKC; ++rc, ++slot_it) {
+          const int s = slot_it & 1;
+          mbar_wait(&slot_full[s], (slot_it >> 1) & 1);
+          tc_fence_after();
+          const uint64_t da = make_desc_sw128(smem_u32(sE + rc * kChunk));
+          const uint64_t db = make_desc_sw128(smem_u32(sRing + s * kSlot));
+          const int ks = (rc == RKC - 1) ? last_ks : 4;
+          for (int kk = 0; kk < ks; ++kk) umma_f16(tmem + 256, da + 2 * kk, db + 2 * kk, idesc2, (rc | kk) ? 1u : 0u);
+          umma_commit(&slot_empty[s]);
+        }
+        umma_commit(&v_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warpgroups =====================
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int lrow = q * 32 + lane;               // TMEM lane: region within the M-tile / word row
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int etid = threadIdx.x - 128;
+    int tile_it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tile_it) {
+      const int b = tile / nct, c = tile - b * nct;
+      const int ncap = p.tile_ncap[c], first = p.tile_first[c];
+      if (etid < ncap) {
+        cap_off_s[etid] = p.cap_row[first + etid] - c * kTileN;
+        cap_len_s[etid] = min(max(p.cap_lens[first + etid], 0), p.T);
+      }
+      named_bar_sync(1, 384);
+      // ---- epilogue 1: both softmaxes of M-tile wg -------------------------------------------
+      if (wg < NMT) {
+        const uint32_t sbuf_it = (uint32_t)tile_it * NMT + wg;
+        const int buf = sbuf_it & 1;
+        mbar_wait(&s_full[wg], tile_it & 1);
+        tc_fence_after();
+        const int r = wg * 128 + lrow;
+        for (int cc = 0; cc < ncap; ++cc) {
+          const int off = cap_off_s[cc], L = cap_len_s[cc];
+          if (L == 0) continue;
+          const uint32_t taddr = tmem + lane_addr + buf * 128 + off;
+          switch ((L + 7) >> 3) {
+            case 1: caption_softmax<T16, 8>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
+            case 2: caption_softmax<T16, 16>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
+            case 3: caption_softmax<T16, 24>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
+            default: caption_softmax<T16, 32>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
+      }
+      fence_proxy_async();   // e (generic-proxy stores) -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&e_ready);
+      // ---- epilogue 2: cosine per word, log-sum-exp per caption --------------------------------
+      mbar_wait(&v_full, tile_it & 1);
+      mbar_wait(&w_full, tile_it & 1);   // the TMA-written word tile is read below through the generic proxy
+      tc_fence_after();
+      float accn = 0.f, accq = 0.f;
+      for (int ch = wg; ch < 8; ch += 3) {
+        float v[32];
+        tmem_ld32(tmem + lane_addr + 256 + ch * 32, v);
+        tmem_ld_wait();
+        const unsigned char* wrow = sW + (size_t)(ch >> 1) * kChunk + lrow * 128;
+        const int u0 = (ch & 1) * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint4 wv = *reinterpret_cast<const uint4*>(wrow + ((((u0 + u) ^ (lrow & 7)) & 7) << 4));
+          const uint32_t wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 w2 = unpack2<T16>(wr[k]);
+            accn = fmaf(w2.x, v[u * 8 + 2 * k], accn);
+            accn = fmaf(w2.y, v[u * 8 + 2 * k + 1], accn);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) accq = fmaf(v[k], v[k], accq);
+      }
+      part_s[wg][lrow] = make_float2(accn, accq);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&v_empty);   // V drained from TMEM
+        mbar_arrive(&w_empty);   // word tile no longer read
+      }
+      named_bar_sync(1, 384);
+      if (wg == 0) {
+        const float2 a = part_s[0][lrow], b2 = part_s[1][lrow], c2 = part_s[2][lrow];
+        const float nn = a.x + b2.x + c2.x;
+        const float qq = sqrtf(a.y + b2.y + c2.y);
+        const float den = fmaxf(p.pn[(size_t)c * kTileN + lrow] * qq, 1e-30f);
+        cos_s[lrow] = nn / den;
+        named_bar_sync(2, 128);
+        if (lrow < ncap) {
+          const int off = cap_off_s[lrow], L = cap_len_s[lrow];
+          float sum = 0.f;
+          for (int t = 0; t < L; ++t) sum += __expf(p.gamma2 * cos_s[off + t]);
+          p.m_out[(size_t)b * p.Bc + first + lrow] = logf(sum);                      // words_loss.py:77-79
+        }
+      }
+      named_bar_sync(1, 384);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct TcPlan {
+  int nt_max;
+  size_t off_Wh, off_pn, off_caprow, off_tfirst, off_tncap, off_ntiles, off_Ct, off_Ck, off_attS, off_attB, off_bwd, total;
+};
+
+static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
+  TcPlan p;
+  const int per_tile = 128 / T;  // captions that always fit in one tile
+  p.nt_max = (Bc + per_tile - 1) / per_tile;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 1024); return at; };
+  p.off_Wh = take((size_t)p.nt_max * kTileN * kD * 2);
+  p.off_pn = take((size_t)p.nt_max * kTileN * 4);
+  p.off_caprow = take((size_t)Bc * 4);
+  p.off_tfirst = take((size_t)p.nt_max * 4);
+  p.off_tncap = take((size_t)p.nt_max * 4);
+  p.off_ntiles = take(256);
+  p.off_Ct = take((size_t)Bi * kRRows * kD * 2);
+  p.off_Ck = take((size_t)Bi * kD * kRCols * 2);
+  p.off_attS = take((size_t)Bi * T * R * 4);
+  p.off_attB = take((size_t)Bi * T * R * 4);
+  p.off_bwd = o;
+  o += damsm_fp32_workspace_bytes(Bi, Bc, T, D, R);   // backward still runs on the fp32 path
+  p.total = o;
+  return p;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <typename T16>
+static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                   const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1, float gamma2, float* m_out,
+                   char* ws, const TcPlan& pl, cudaStream_t st) {
+  T16* Wh = (T16*)(ws + pl.off_Wh);
+  float* pn = (float*)(ws + pl.off_pn);
+  int32_t* cap_row = (int32_t*)(ws + pl.off_caprow);
+  int32_t* tfirst = (int32_t*)(ws + pl.off_tfirst);
+  int32_t* tncap = (int32_t*)(ws + pl.off_tncap);
+  int32_t* ntiles = (int32_t*)(ws + pl.off_ntiles);
+  T16* Ct = (T16*)(ws + pl.off_Ct);
+  T16* Ck = (T16*)(ws + pl.off_Ck);
+  AGB_CUDA(cudaMemsetAsync(Wh, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
+  AGB_CUDA(cudaMemsetAsync(pn, 0, (size_t)pl.nt_max * kTileN * 4, st));
+  tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, cap_row, tfirst, tncap, ntiles);
+  if (int rc = check_launch("tile_pack_kernel")) return rc;
+  pack_words_kernel_tc<T16><<<dim3(Bc, T), 128, 0, st>>>(words, ws_b, ws_d, ws_t, cap_lens, cap_row, Wh, pn, T);
+  if (int rc = check_launch("pack_words_kernel_tc")) return rc;
+  pack_img_kernel_tc<T16><<<dim3(kRRows / 32, kD / 32, Bi), dim3(32, 8), 0, st>>>(img, Ck, Ct, R);
+  if (int rc = check_launch("pack_img_kernel_tc")) return rc;
+  const bool bf = std::is_same<T16, __nv_bfloat16>::value;
+  CUtensorMap mapW, mapCt, mapCk;
+  if (int rc = make_tmap_2d(&mapW, Wh, (uint64_t)pl.nt_max * kTileN, kD, 128, bf)) return rc;
+  if (int rc = make_tmap_2d(&mapCt, Ct, (uint64_t)Bi * kRRows, kD, 128, bf)) return rc;
+  if (int rc = make_tmap_2d(&mapCk, Ck, (uint64_t)Bi * kD, kRCols, 256, bf)) return rc;
+  FwdParams p;
+  p.tile_first = tfirst; p.tile_ncap = tncap; p.ntiles = ntiles; p.cap_row = cap_row; p.cap_lens = cap_lens;
+  p.pn = pn; p.m_out = m_out; p.Bi = Bi; p.Bc = Bc; p.T = T; p.R = R;
+  p.scale_log2 = kLog2e / sqrtf((float)kD);
+  p.g1_log2 = gamma1 * kLog2e;
+  p.gamma2 = gamma2;
+  auto kern = damsm_fwd_kernel<T16>;
+  AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const long long max_items = (long long)Bi * pl.nt_max;
+  const int grid = (int)std::min<long long>(num_sms(), max_items);
+  const int slot = prof_begin(PROF_DAMSM_TC_FWD, st);
+  kern<<<grid, kThreads, kSmemBytes, st>>>(mapW, mapCt, mapCk, p);
+  prof_end(slot, st);
+  return check_launch("damsm_fwd_kernel");
+}
+
+}  // namespace tc
+
+int damsm_tc_supported(int T, int D, int R) { return (D == tc::kD && T >= 1 && T <= 32 && R >= 1 && R <= tc::kRCols) ? 1 : 0; }
+
+size_t damsm_tc_workspace_bytes(int Bi, int Bc, int T, int D, int R) { return tc::make_tc_plan(Bi, Bc, T, D, R).total; }
+
+int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                 const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
+                 float eps, int row_offset, float* m_out, float* att_out, const float* cnn, const float* rnn,
+                 float* scos_out, void* workspace, size_t workspace_bytes, int math, cudaStream_t st) {
+  if (Bi <= 0 || Bc <= 0) return fail_arg("non-positive batch");
+  if (Bi > 65535) return fail_unsupported("Bi=%d > 65535", Bi);
+  if (math == AGB_MATH_TC_F16 && gamma1 > 11.f) return fail_unsupported("gamma1=%g overflows fp16 (use bf16 or fp32 math)", gamma1);
+  const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R);
+  if (workspace_bytes < pl.total) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
+    return AGB_E_WORKSPACE;
+  }
+  char* ws = (char*)workspace;
+  int rc;
+  if (math == AGB_MATH_TC_BF16)
+    rc = tc::run_fwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, st);
+  else
+    rc = tc::run_fwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, st);
+  if (rc) return rc;
+  if (att_out) {
+    if (row_offset < 0 || row_offset + Bi > Bc) return fail_arg("row_offset=%d out of range", row_offset);
+    rc = damsm_diag_att_maps(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, T, D, R, gamma1, row_offset, att_out,
+                             (float*)(ws + pl.off_attS), (float*)(ws + pl.off_attB), st);
+    if (rc) return rc;
+  }
+  if (cnn) return sent_cos_fwd_launch(cnn, rnn, Bi, Bc, D, eps, scos_out, st);
+  return 0;
+}
+
+int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                 const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
+                 float eps, const float* dm, const float* gscale, float* dimg, float* dwords, void* workspace,
+                 size_t workspace_bytes, int math, cudaStream_t st) {
+  // Round 1: the backward of the tensor-core mode still runs the fp32 CUDA-core kernels.
+  const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R);
+  if (workspace_bytes < pl.total) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
+    return AGB_E_WORKSPACE;
+  }
+  return damsm_fp32_bwd(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, D, R, gamma1, gamma2, eps, dm, gscale,
+                        dimg, dwords, (char*)workspace + pl.off_bwd, workspace_bytes - pl.off_bwd, st);
+}
+
+}  // namespace agb

@@ -22,6 +22,8 @@ SIGNATURES = {
     "agb_last_error": (c_char_p, []),
     "agb_has_tcgen05": (c_int, []),
     "agb_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "agb_tc_gemm_test": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
     "agb_launch_count": (ctypes.c_longlong, []),
     "agb_prof_enable": (None, [c_int]),
     "agb_prof_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),

@@ -22,6 +22,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                  bool bf16);
 
+constexpr int kChunkBytes16 = 128 * 128;   // one [128 x 64] 16-bit swizzled tile
+
+// batched GEMM on tcgen05 (tc_gemm.cu):  C[z][m,n] (+)= alpha * sum_kb sum_k A[z][kb][m,k] B[z][kb][n,k]
+struct TcGemmArgs {
+  int a_mn, b_mn;              // 0: K-major array (rows = m|n, cols = k), 1: MN-major (rows = k, cols = m|n)
+  int bf16;                    // operand type: 0 = fp16, 1 = bf16
+  int M, N, K, KB, NT;         // K % 64 == 0; NT = 64 or 128 output columns per CTA
+  int64_t a_zrow, a_zcol, a_kbrow, a_kbcol;   // offsets into map A per batch z / reduction block kb
+  int64_t b_zrow, b_zcol, b_kbrow, b_kbcol;
+  float* C;
+  int64_t c_z, c_m, c_n;       // fp32 output strides
+  float alpha;
+  int accumulate;
+};
+int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st);
+
 // ---- PTX wrappers (device) --------------------------------------------------------------------
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -1,0 +1,167 @@
+// Batched 16-bit GEMM on tcgen05 with fp32 accumulation in TMEM and fp32 output:
+//
+//   C[z][m, n] (+)= alpha * sum_{kb < KB} sum_{k < K} A[z][kb][m, k] * B[z][kb][n, k]
+//
+// One CTA per 128 x NT output tile (NT = 64 or 128).  Operands are read by TMA through 2-D tensor
+// maps laid over the whole operand arrays; each operand is either K-major (array rows = m or n,
+// columns = k) or MN-major (array rows = k, columns = m or n), so the transposes that the DAMSM
+// backward needs (d img = dV^T beta, ...) cost nothing.  (z, kb) select sub-matrices through
+// row / column offsets into the maps.  K must be a multiple of 64 (callers pad with zeros);
+// ragged M / N edges are masked at the store.
+//
+// Warp roles: warp 4 = TMA producer, warp 5 = MMA issuer, warps 0-3 = epilogue (TMEM -> global).
+#include "tc_common.cuh"
+
+namespace agb {
+namespace tc {
+
+constexpr int kGemmStages = 6;
+constexpr int kGemmStageBytes = 2 * kChunkBytes16;   // A chunk + B chunk, 16 KB each
+constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024;
+
+// SWIZZLE_128B descriptor for an MN-major operand: tile = [k rows][64 mn elements], 8-row groups
+// 1024 B apart (SBO), successive 64-wide mn blocks `lbo_bytes` apart (LBO)
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const TcGemmArgs g) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[kGemmStages], empty[kGemmStages], done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * g.NT, m0 = blockIdx.y * 128, z = blockIdx.z;
+  const int kchunks = g.K >> 6;
+  const int total = g.KB * kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGemmStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      const uint32_t bytes = (uint32_t)kChunkBytes16 + (uint32_t)g.NT * 128u;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % kGemmStages, use = it / kGemmStages;
+        const int kb = it / kchunks, k0 = (it - kb * kchunks) * 64;
+        mbar_wait(&empty[s], (use & 1) ^ 1);
+        mbar_expect_tx(&full[s], bytes);
+        unsigned char* sa = smem + s * kGemmStageBytes;
+        unsigned char* sb = sa + kChunkBytes16;
+        const int arow = (int)(z * g.a_zrow + kb * g.a_kbrow), acol = (int)(z * g.a_zcol + kb * g.a_kbcol);
+        const int brow = (int)(z * g.b_zrow + kb * g.b_kbrow), bcol = (int)(z * g.b_zcol + kb * g.b_kbcol);
+        if (!g.a_mn) {
+          tma_load_2d(sa, &mapA, &full[s], acol + k0, arow + m0);                 // [128 m][64 k]
+        } else {
+          tma_load_2d(sa, &mapA, &full[s], acol + m0, arow + k0);                 // [64 k][64 m] x 2
+          tma_load_2d(sa + 8192, &mapA, &full[s], acol + m0 + 64, arow + k0);
+        }
+        if (!g.b_mn) {
+          tma_load_2d(sb, &mapB, &full[s], bcol + k0, brow + n0);                 // [NT n][64 k]
+        } else {
+          for (int nb = 0; nb < g.NT / 64; ++nb)
+            tma_load_2d(sb + nb * 8192, &mapB, &full[s], bcol + n0 + nb * 64, brow + k0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(128, g.NT, g.bf16) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % kGemmStages, use = it / kGemmStages;
+        mbar_wait(&full[s], use & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * kGemmStageBytes), sb = sa + kChunkBytes16;
+        for (int kk = 0; kk < 4; ++kk) {
+          // K-major: +32 B per 16 k inside the 128-B row; MN-major: +16 rows = 2048 B
+          const uint64_t da = g.a_mn ? make_desc_sw128_mn(sa + kk * 2048, 8192) : make_desc_sw128(sa) + 2 * kk;
+          const uint64_t db = g.b_mn ? make_desc_sw128_mn(sb + kk * 2048, 8192) : make_desc_sw128(sb) + 2 * kk;
+          umma_f16(tmem, da, db, idesc, (it | kk) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(&done);
+    }
+  } else if (warp < 4) {
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    float* Cz = g.C + (int64_t)z * g.c_z;
+    for (int c0 = 0; c0 < g.NT; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (m < g.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < g.N) {
+            float* p = Cz + (int64_t)m * g.c_m + (int64_t)n * g.c_n;
+            const float x = g.alpha * v[j];
+            *p = g.accumulate ? (*p + x) : x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
+  if (g.K <= 0 || g.K % 64 || g.KB <= 0) return fail_arg("tc_gemm: K=%d must be a positive multiple of 64", g.K);
+  if (g.NT != 64 && g.NT != 128) return fail_arg("tc_gemm: NT=%d", g.NT);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AGB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(g.N, g.NT), cdiv(g.M, 128), batch);
+  if (grid.y > 65535 || grid.z > 65535) return fail_unsupported("tc_gemm grid too large");
+  const int slot = prof_begin(PROF_DAMSM_TC_BWD, st);
+  tc_gemm_kernel<<<grid, 192, kGemmSmem, st>>>(mapA, mapB, g);
+  prof_end(slot, st);
+  return check_launch("tc_gemm_kernel");
+}
+
+}  // namespace tc
+}  // namespace agb
+
+using namespace agb;
+
+// Test hook: C[M,N] = A * B^T for one batch.  A is [M,K] row-major (a_mn = 0) or [K,M] (a_mn = 1);
+// B likewise with N.  M, N arbitrary (<= one grid), K % 64 == 0.
+extern "C" int agb_tc_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mn, int b_mn,
+                                int bf16, int accumulate, void* stream) {
+  if (!A || !B || !C) return fail_arg("null pointer");
+  CUtensorMap mapA, mapB;
+  const int NT = (N % 128 == 0 || N > 64) ? 128 : 64;
+  // box rows: K-major operands load [128 or NT rows x 64]; MN-major operands load [64 k rows x 64]
+  if (int rc = tc::make_tmap_2d(&mapA, A, a_mn ? K : M, a_mn ? M : K, a_mn ? 64 : 128, bf16 != 0)) return rc;
+  if (int rc = tc::make_tmap_2d(&mapB, B, b_mn ? K : N, b_mn ? N : K, b_mn ? 64 : NT, bf16 != 0)) return rc;
+  tc::TcGemmArgs g{};
+  g.a_mn = a_mn; g.b_mn = b_mn; g.bf16 = bf16 ? 1 : 0; g.M = M; g.N = N; g.K = K; g.KB = 1; g.NT = NT;
+  g.C = C; g.c_z = 0; g.c_m = N; g.c_n = 1; g.alpha = 1.f; g.accumulate = accumulate;
+  return tc::tc_gemm(g, mapA, mapB, 1, (cudaStream_t)stream);
+}

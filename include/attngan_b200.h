@@ -63,6 +63,12 @@ int agb_has_tcgen05(void);
 int agb_tc_selftest(const void* A, const void* B, float* C, int N, int K, int bf16, int manual_a,
                     void* stream);
 
+/* Test hook of the batched tcgen05 GEMM (tc_gemm.cu): C[M,N] (+)= A * B^T for one batch, fp32 out.
+ * A is [M,K] row-major (a_mn = 0, K-major) or [K,M] (a_mn = 1, MN-major); B likewise with N.
+ * K % 64 == 0; operand row pitches must be multiples of 16 bytes. */
+int agb_tc_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mn, int b_mn,
+                     int bf16, int accumulate, void* stream);
+
 long long agb_launch_count(void);
 void agb_prof_enable(int on);
 int agb_prof_read(int tag, double* total_ms, long long* launches);

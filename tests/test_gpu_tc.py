@@ -32,6 +32,29 @@ def test_tcgen05_building_blocks(agb, N, K, bf16, manual_a):
     assert err < 1e-5, f"tcgen05 GEMM mismatch: rel err {err:.3e}"
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 320, 256), (296, 256, 384), (72, 64, 128)])
+@pytest.mark.parametrize("bf16", [0, 1])
+def test_tc_gemm_all_majors(agb, a_mn, b_mn, M, N, K, bf16):
+    """batched tcgen05 GEMM: K-major and MN-major operands, ragged M/N edges, accumulate"""
+    g = torch.Generator().manual_seed(M + N + K)
+    dt = torch.bfloat16 if bf16 else torch.float16
+    A = torch.randn(M, K, generator=g).to(dt)
+    B = torch.randn(N, K, generator=g).to(dt)
+    Ad = (A.t().contiguous() if a_mn else A).cuda()
+    Bd = (B.t().contiguous() if b_mn else B).cuda()
+    C0 = torch.randn(M, N, generator=g)
+    C = C0.clone().cuda()
+    lib = agb.native.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    agb.native.check(lib.agb_tc_gemm_test(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, a_mn, b_mn, bf16, 1, st),
+                     "agb_tc_gemm_test")
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double() @ B.double().T
+    err = (C.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, f"rel err {err:.3e}"
+
+
 # ------------------------------------------------------------------------------------------------
 # fused tcgen05 DAMSM kernels (AGB_MATH_TC_F16 / _BF16) against the oracle
 # ------------------------------------------------------------------------------------------------

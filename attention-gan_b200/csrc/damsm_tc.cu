@@ -417,7 +417,11 @@ damsm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 struct TcPlan {
   int nt_max;
-  size_t off_Wh, off_pn, off_caprow, off_tfirst, off_tncap, off_ntiles, off_Ct, off_Ck, off_attS, off_attB, off_bwd, total;
+  size_t off_Wh, off_pn, off_caprow, off_tfirst, off_tncap, off_ntiles, off_Ct, off_Ck, off_attS, off_attB;
+  // staged backward, per chunk of ct tiles (N = ct*128 word rows) and all Bi images
+  int ct;        // tiles per chunk
+  int splits;    // slices of the image range in the dW GEMM
+  size_t off_S32, off_E16, off_V32, off_dV16, off_G32, off_DS16, off_A116, off_stat, off_dwp, total;
 };
 
 static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
@@ -436,8 +440,22 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_Ck = take((size_t)Bi * kD * kRCols * 2);
   p.off_attS = take((size_t)Bi * T * R * 4);
   p.off_attB = take((size_t)Bi * T * R * 4);
-  p.off_bwd = o;
-  o += damsm_fp32_workspace_bytes(Bi, Bc, T, D, R);   // backward still runs on the fp32 path
+  const size_t tile_bytes = (size_t)Bi * kTileN * (kRCols * (4 + 2 + 4 + 2 + 2) + kD * (4 + 2) + 16);
+  size_t ct = ((size_t)4 << 30) / tile_bytes;
+  if (ct < 1) ct = 1;
+  if (ct > (size_t)p.nt_max) ct = p.nt_max;
+  p.ct = (int)ct;
+  p.splits = std::min(Bi, 16);
+  const size_t rows = (size_t)Bi * ct * kTileN;
+  p.off_S32 = take(rows * kRCols * 4);
+  p.off_E16 = take(rows * kRCols * 2);
+  p.off_V32 = take(rows * kD * 4);
+  p.off_dV16 = take(rows * kD * 2);
+  p.off_G32 = take(rows * kRCols * 4);
+  p.off_DS16 = take(rows * kRCols * 2);
+  p.off_A116 = take(rows * kRCols * 2);
+  p.off_stat = take(rows * 16);
+  p.off_dwp = take((size_t)p.splits * ct * kTileN * kD * 4);
   p.total = o;
   return p;
 }
@@ -453,10 +471,15 @@ static int num_sms() {
   return g_num_sms;
 }
 
+struct Packed {
+  void* Wh; float* pn; int32_t *cap_row, *tfirst, *tncap, *ntiles; void* Ct; void* Ck;
+};
+
+// pack the operands of one call: caption tiles, 16-bit words, 16-bit region features (both layouts)
 template <typename T16>
-static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
-                   const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1, float gamma2, float* m_out,
-                   char* ws, const TcPlan& pl, cudaStream_t st) {
+static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                    const int32_t* cap_lens, int Bi, int Bc, int T, int R, char* ws, const TcPlan& pl, Packed* out,
+                    cudaStream_t st) {
   T16* Wh = (T16*)(ws + pl.off_Wh);
   float* pn = (float*)(ws + pl.off_pn);
   int32_t* cap_row = (int32_t*)(ws + pl.off_caprow);
@@ -473,14 +496,25 @@ static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t w
   if (int rc = check_launch("pack_words_kernel_tc")) return rc;
   pack_img_kernel_tc<T16><<<dim3(kRRows / 32, kD / 32, Bi), dim3(32, 8), 0, st>>>(img, Ck, Ct, R);
   if (int rc = check_launch("pack_img_kernel_tc")) return rc;
+  out->Wh = Wh; out->pn = pn; out->cap_row = cap_row; out->tfirst = tfirst; out->tncap = tncap; out->ntiles = ntiles;
+  out->Ct = Ct; out->Ck = Ck;
+  return 0;
+}
+
+template <typename T16>
+static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
+                   const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1, float gamma2, float* m_out,
+                   char* ws, const TcPlan& pl, cudaStream_t st) {
+  Packed pk;
+  if (int rc = run_pack<T16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, ws, pl, &pk, st)) return rc;
   const bool bf = std::is_same<T16, __nv_bfloat16>::value;
   CUtensorMap mapW, mapCt, mapCk;
-  if (int rc = make_tmap_2d(&mapW, Wh, (uint64_t)pl.nt_max * kTileN, kD, 128, bf)) return rc;
-  if (int rc = make_tmap_2d(&mapCt, Ct, (uint64_t)Bi * kRRows, kD, 128, bf)) return rc;
-  if (int rc = make_tmap_2d(&mapCk, Ck, (uint64_t)Bi * kD, kRCols, 256, bf)) return rc;
+  if (int rc = make_tmap_2d(&mapW, pk.Wh, (uint64_t)pl.nt_max * kTileN, kD, 128, bf)) return rc;
+  if (int rc = make_tmap_2d(&mapCt, pk.Ct, (uint64_t)Bi * kRRows, kD, 128, bf)) return rc;
+  if (int rc = make_tmap_2d(&mapCk, pk.Ck, (uint64_t)Bi * kD, kRCols, 256, bf)) return rc;
   FwdParams p;
-  p.tile_first = tfirst; p.tile_ncap = tncap; p.ntiles = ntiles; p.cap_row = cap_row; p.cap_lens = cap_lens;
-  p.pn = pn; p.m_out = m_out; p.Bi = Bi; p.Bc = Bc; p.T = T; p.R = R;
+  p.tile_first = pk.tfirst; p.tile_ncap = pk.tncap; p.ntiles = pk.ntiles; p.cap_row = pk.cap_row; p.cap_lens = cap_lens;
+  p.pn = pk.pn; p.m_out = m_out; p.Bi = Bi; p.Bc = Bc; p.T = T; p.R = R;
   p.scale_log2 = kLog2e / sqrtf((float)kD);
   p.g1_log2 = gamma1 * kLog2e;
   p.gamma2 = gamma2;
@@ -493,6 +527,8 @@ static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t w
   prof_end(slot, st);
   return check_launch("damsm_fwd_kernel");
 }
+
+#include "damsm_tc_bwd.inc"
 
 }  // namespace tc
 
@@ -533,14 +569,18 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
                  float eps, const float* dm, const float* gscale, float* dimg, float* dwords, void* workspace,
                  size_t workspace_bytes, int math, cudaStream_t st) {
-  // Round 1: the backward of the tensor-core mode still runs the fp32 CUDA-core kernels.
+  if (Bi <= 0 || Bc <= 0) return fail_arg("non-positive batch");
+  if (Bi > 65535) return fail_unsupported("Bi=%d > 65535", Bi);
   const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R);
   if (workspace_bytes < pl.total) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
     return AGB_E_WORKSPACE;
   }
-  return damsm_fp32_bwd(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, D, R, gamma1, gamma2, eps, dm, gscale,
-                        dimg, dwords, (char*)workspace + pl.off_bwd, workspace_bytes - pl.off_bwd, st);
+  if (math == AGB_MATH_TC_BF16)
+    return tc::run_bwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale,
+                                      dimg, dwords, (char*)workspace, pl, st);
+  return tc::run_bwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale, dimg,
+                             dwords, (char*)workspace, pl, st);
 }
 
 }  // namespace agb

@@ -35,6 +35,13 @@ struct TcGemmArgs {
   int64_t c_z, c_m, c_n;       // fp32 output strides
   float alpha;
   int accumulate;
+  // data-dependent extent: valid = clamp((*dyn_tiles - dyn_t0) * 128, 0, extent) rows of dimension
+  // dyn_dim (0 = none, 1 = M, 3 = K); CTAs / K-chunks beyond it do no work
+  const int32_t* dyn_tiles;
+  int dyn_t0, dyn_dim;
+  // split_kb != 0: blockIdx.z enumerates slices of the kb range (kb = z*KB + i < kb_total) instead of
+  // independent batches; slice z writes its partial sum to C + z*c_z
+  int split_kb, kb_total;
 };
 int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st);
 

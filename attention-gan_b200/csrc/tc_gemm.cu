@@ -40,8 +40,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * g.NT, m0 = blockIdx.y * 128, z = blockIdx.z;
-  const int kchunks = g.K >> 6;
-  const int total = g.KB * kchunks;
+  int kchunks = g.K >> 6;
+  int kb_begin = 0, kb_count = g.KB;
+  const int zb = g.split_kb ? 0 : z;                   // batch index used for operand offsets
+  if (g.split_kb) {
+    kb_begin = z * g.KB;
+    kb_count = max(0, min(g.KB, g.kb_total - kb_begin));
+  }
+  int m_valid = g.M;
+  if (g.dyn_dim) {
+    const int valid = max(0, (g.dyn_tiles[0] - g.dyn_t0) * 128);
+    if (g.dyn_dim == 1) m_valid = min(g.M, valid);
+    else kchunks = min(kchunks, (valid + 63) >> 6);
+  }
+  if (m0 >= m_valid) return;                           // whole CTA: nothing to do (before any barrier / alloc)
+  const int total = kb_count * kchunks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) {
@@ -62,13 +75,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t bytes = (uint32_t)kChunkBytes16 + (uint32_t)g.NT * 128u;
       for (int it = 0; it < total; ++it) {
         const int s = it % kGemmStages, use = it / kGemmStages;
-        const int kb = it / kchunks, k0 = (it - kb * kchunks) * 64;
+        const int kbl = it / kchunks, k0 = (it - kbl * kchunks) * 64;
+        const int kb = kb_begin + kbl;
         mbar_wait(&empty[s], (use & 1) ^ 1);
         mbar_expect_tx(&full[s], bytes);
         unsigned char* sa = smem + s * kGemmStageBytes;
         unsigned char* sb = sa + kChunkBytes16;
-        const int arow = (int)(z * g.a_zrow + kb * g.a_kbrow), acol = (int)(z * g.a_zcol + kb * g.a_kbcol);
-        const int brow = (int)(z * g.b_zrow + kb * g.b_kbrow), bcol = (int)(z * g.b_zcol + kb * g.b_kbcol);
+        const int arow = (int)(zb * g.a_zrow + kb * g.a_kbrow), acol = (int)(zb * g.a_zcol + kb * g.a_kbcol);
+        const int brow = (int)(zb * g.b_zrow + kb * g.b_kbrow), bcol = (int)(zb * g.b_zcol + kb * g.b_kbcol);
         if (!g.a_mn) {
           tma_load_2d(sa, &mapA, &full[s], acol + k0, arow + m0);                 // [128 m][64 k]
         } else {
@@ -102,15 +116,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       umma_commit(&done);
     }
   } else if (warp < 4) {
-    mbar_wait(&done, 0);
-    tc_fence_after();
+    if (total > 0) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+    }
     const int m = m0 + warp * 32 + lane;
     float* Cz = g.C + (int64_t)z * g.c_z;
     for (int c0 = 0; c0 < g.NT; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      if (m < g.M) {
+      if (total > 0) {
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;       // empty reduction: the sum is zero
+      }
+      if (m < m_valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n0 + c0 + j;

@@ -126,8 +126,9 @@ def test_tc_words_loss_cfg2(agb, math):
     tol = 1e-4 if math == "f16" else 1e-3
     assert abs(wl.item() - wl0) <= tol * abs(wl0), (wl.item(), wl0)
     wl.backward()
-    assert _rel(im.grad, dc0.reshape(img.shape)) < 5e-3
-    assert _rel(wd.grad, dw0) < 5e-3
+    gtol = 5e-3 if math == "f16" else 2e-2          # bf16 operands carry 8 significand bits
+    assert _rel(im.grad, dc0.reshape(img.shape)) < gtol
+    assert _rel(wd.grad, dw0) < gtol
 
 
 def test_tc_row_blocks_and_ragged_lengths(agb):

@@ -42,6 +42,7 @@ struct TcGemmArgs {
   // split_kb != 0: blockIdx.z enumerates slices of the kb range (kb = z*KB + i < kb_total) instead of
   // independent batches; slice z writes its partial sum to C + z*c_z
   int split_kb, kb_total;
+  int stages;                  // ring depth, set by tc_gemm()
 };
 int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st);
 

@@ -10,6 +10,8 @@
 // ragged M / N edges are masked at the store.
 //
 // Warp roles: warp 4 = TMA producer, warp 5 = MMA issuer, warps 0-3 = epilogue (TMEM -> global).
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace agb {
@@ -31,7 +33,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint3
   return d;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const TcGemmArgs g) {
   extern __shared__ unsigned char smem_dyn[];
@@ -55,9 +57,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   if (m0 >= m_valid) return;                           // whole CTA: nothing to do (before any barrier / alloc)
   const int total = kb_count * kchunks;
+  const int stages = g.stages;
+  const int stage_bytes = kChunkBytes16 + g.NT * 128;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kGemmStages; ++i) {
+    for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -74,12 +78,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (elect_one()) {
       const uint32_t bytes = (uint32_t)kChunkBytes16 + (uint32_t)g.NT * 128u;
       for (int it = 0; it < total; ++it) {
-        const int s = it % kGemmStages, use = it / kGemmStages;
+        const int s = it % stages, use = it / stages;
         const int kbl = it / kchunks, k0 = (it - kbl * kchunks) * 64;
         const int kb = kb_begin + kbl;
         mbar_wait(&empty[s], (use & 1) ^ 1);
         mbar_expect_tx(&full[s], bytes);
-        unsigned char* sa = smem + s * kGemmStageBytes;
+        unsigned char* sa = smem + s * stage_bytes;
         unsigned char* sb = sa + kChunkBytes16;
         const int arow = (int)(zb * g.a_zrow + kb * g.a_kbrow), acol = (int)(zb * g.a_zcol + kb * g.a_kbcol);
         const int brow = (int)(zb * g.b_zrow + kb * g.b_kbrow), bcol = (int)(zb * g.b_zcol + kb * g.b_kbcol);
@@ -101,10 +105,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (elect_one()) {
       const uint32_t idesc = make_idesc(128, g.NT, g.bf16) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16);
       for (int it = 0; it < total; ++it) {
-        const int s = it % kGemmStages, use = it / kGemmStages;
+        const int s = it % stages, use = it / stages;
         mbar_wait(&full[s], use & 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * kGemmStageBytes), sb = sa + kChunkBytes16;
+        const uint32_t sa = smem_u32(smem + s * stage_bytes), sb = sa + kChunkBytes16;
         for (int kk = 0; kk < 4; ++kk) {
           // K-major: +32 B per 16 k inside the 128-B row; MN-major: +16 rows = 2048 B
           const uint64_t da = g.a_mn ? make_desc_sw128_mn(sa + kk * 2048, 8192) : make_desc_sw128(sa) + 2 * kk;
@@ -132,13 +136,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j = 0; j < 32; ++j) v[j] = 0.f;       // empty reduction: the sum is zero
       }
       if (m < m_valid) {
+        float* prow = Cz + (int64_t)m * g.c_m + (int64_t)(n0 + c0) * g.c_n;
+        if (g.c_n == 1 && n0 + c0 + 32 <= g.N && ((uintptr_t)prow & 15) == 0) {
+          // 32 consecutive fp32 of one output row: eight 16-byte stores per thread
+          float4* p4 = reinterpret_cast<float4*>(prow);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < g.N) {
-            float* p = Cz + (int64_t)m * g.c_m + (int64_t)n * g.c_n;
-            const float x = g.alpha * v[j];
-            *p = g.accumulate ? (*p + x) : x;
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(g.alpha * v[4 * j], g.alpha * v[4 * j + 1], g.alpha * v[4 * j + 2], g.alpha * v[4 * j + 3]);
+            if (g.accumulate) {
+              const float4 o = p4[j];
+              x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+            }
+            p4[j] = x;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < g.N) {
+              float* p = Cz + (int64_t)m * g.c_m + (int64_t)n * g.c_n;
+              const float x = g.alpha * v[j];
+              *p = g.accumulate ? (*p + x) : x;
+            }
           }
         }
       }
@@ -149,7 +168,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st) {
+int tc_gemm(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st) {
+  TcGemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
   if (g.K <= 0 || g.K % 64 || g.KB <= 0) return fail_arg("tc_gemm: K=%d must be a positive multiple of 64", g.K);
   if (g.NT != 64 && g.NT != 128) return fail_arg("tc_gemm: NT=%d", g.NT);
@@ -160,8 +180,12 @@ int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& map
   }
   dim3 grid(cdiv(g.N, g.NT), cdiv(g.M, 128), batch);
   if (grid.y > 65535 || grid.z > 65535) return fail_unsupported("tc_gemm grid too large");
+  // short reductions get a short ring so that several CTAs share an SM and hide each other's prologue
+  const long long chunks = (long long)g.KB * (g.K / 64);
+  g.stages = (int)std::min<long long>(kGemmStages, std::max<long long>(2, chunks));
+  const int smem_bytes = g.stages * (kChunkBytes16 + g.NT * 128) + 1024;
   const int slot = prof_begin(PROF_DAMSM_TC_BWD, st);
-  tc_gemm_kernel<<<grid, 192, kGemmSmem, st>>>(mapA, mapB, g);
+  tc_gemm_kernel<<<grid, 192, smem_bytes, st>>>(mapA, mapB, g);
   prof_end(slot, st);
   return check_launch("tc_gemm_kernel");
 }

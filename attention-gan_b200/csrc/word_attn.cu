@@ -14,6 +14,12 @@
 
 namespace agb {
 
+namespace tc {
+int word_attn_tc_supported(const void* images, int C, int HW, int T, int io_dtype);
+int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, void* ctx, int64_t ctx_bs, void* attn,
+                     int B, int C, int HW, int T, int io_dtype, float qscale, cudaStream_t st);
+}  // namespace tc
+
 constexpr int kAttnThreads = 128;
 
 // ---------------------------------------------------------------------------------------------
@@ -493,6 +499,10 @@ extern "C" int agb_word_attn_fwd(const void* images, const float* words, int64_t
   word_proj_fwd_kernel<<<B, 256, 0, st>>>(words, ws_b, ws_e, ws_t, conv_w, we, C, E, T);
   if (int rc = check_launch("word_proj_fwd_kernel")) return rc;
   const float qscale = (scaled ? 1.f / sqrtf((float)C) : 1.f) * kLog2e;
+  // 16-bit feature maps: both contractions on tcgen05 (word_attn_tc.cu); fp32 maps and odd shapes:
+  // CUDA cores.  Both are native sm_100a kernels of this library.
+  if (tc::word_attn_tc_supported(images, C, HW, T, io_dtype))
+    return tc::word_attn_fwd_tc(images, we, mask, ctx, ctx_bs, attn, B, C, HW, T, io_dtype, qscale, st);
   const int use_tma = ((C * T) % 4 == 0) && ((uintptr_t)we % 16 == 0);
   const int tm = pick_tmax(T);
   int rc = 0;

@@ -1,0 +1,314 @@
+// Generator word-context attention on tcgen05 for 16-bit I/O (bf16 / fp16 feature maps).
+//
+// Replaces AttentionModule.forward (reference networks/attention.py:25-79).  At C = 32, T = 18 the
+// CUDA-core formulation needs 1152 FMA per pixel forward against 164 B of HBM traffic, which puts
+// its ceiling (fp32 FMA rate) below the HBM roofline; the two tiny contractions therefore run on
+// the tensor cores and the SM only does the softmax and the stores:
+//
+//   tile       = 128 consecutive pixels of one sample (NCHW, HW contiguous)
+//   TMA        h tile [C rows x 128 px] -> smem, 128B swizzle; used as the MN-major A operand
+//   GEMM1      S[px, t]   = sum_c h[c, px] * (W.e)[c, t] * scale*log2(e)      (B operand: hi + lo split,
+//                            so W.e enters with fp32 accuracy)                  M=128, N=NT, K=C
+//   epilogue 1 thread = pixel: mask, softmax over the T words in registers (exp2), attn -> global,
+//              P = attn as fp16 written back into TMEM (tcgen05.st) over the scores
+//   GEMM2      ctx[px, c] = sum_t P[px, t] * (W.e)[c, t]        A operand from TMEM    M=128, N=C, K=NT
+//   epilogue 2 thread = pixel: ctx -> global (lanes = consecutive pixels: coalesced)
+//
+// TMEM: 2 tile buffers x (NT score/P columns + C context columns) = 128 columns per CTA at
+// T <= 32, C <= 32 (256 otherwise), so up to 4 CTAs share an SM and each keeps two tiles in flight.  Warps: 0 = TMA, 1 = MMA, 2-5 = epilogue.
+#include <algorithm>
+#include <type_traits>
+
+#include "tc_common.cuh"
+
+namespace agb {
+namespace tc {
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t make_desc_sw128_mn_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <typename T16> __device__ __forceinline__ T16 f2h(float v);
+template <> __device__ __forceinline__ __half f2h<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 f2h<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+struct AttnFwdParams {
+  const float* we;        // [B, C, T] fp32 projected words
+  const int64_t* mask;    // [B, T]
+  void* ctx;              // [B, C, HW] io dtype, batch stride ctx_bs
+  void* attn;             // [B, T, HW] io dtype or null
+  int64_t ctx_bs;
+  int B, C, HW, T;
+  float qscale;           // scale * log2(e)
+  int tiles, ctas_per_sample;
+};
+
+constexpr int kAttnStages = 3;
+
+template <typename IO, int NT>
+__global__ void __launch_bounds__(192)
+word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  const int C = p.C;
+  const int box_bytes = C * 128;                 // one [C x 64 px] box
+  const int stage_bytes = 2 * box_bytes;
+  unsigned char* sH = smem;
+  unsigned char* sB1hi = smem + kAttnStages * stage_bytes;   // [NT rows t][64 k=c]  io type
+  unsigned char* sB1lo = sB1hi + NT * 128;
+  unsigned char* sB2hi = sB1lo + NT * 128;                   // [C rows c][64 k=t]   fp16
+  unsigned char* sB2lo = sB2hi + 64 * 128;
+  __shared__ uint64_t h_full[kAttnStages], h_empty[kAttnStages], s_full[2], p_ready[2], c_full[2], c_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int bufc = NT + C;                       // TMEM columns of one tile buffer: scores/P + context
+  const uint32_t tmem_cols = 2 * bufc <= 128 ? 128u : 256u;
+  const int ntile = (p.tiles - (int)blockIdx.x + p.ctas_per_sample - 1) / p.ctas_per_sample;   // tiles of this CTA
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kAttnStages; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&h_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  // B operands of both GEMMs from W.e of this sample: hi + lo 16-bit split, K-major swizzled rows
+  {
+    const float* we = p.we + (size_t)b * C * p.T;
+    for (int i = threadIdx.x; i < NT * 64; i += blockDim.x) {       // B1[t][c]
+      const int t = i >> 6, c = i & 63;
+      const float x = (t < p.T && c < C) ? we[c * p.T + t] * p.qscale : 0.f;
+      const IO hi = f2h<IO>(x);
+      const IO lo = f2h<IO>(x - to_f32(hi));
+      *reinterpret_cast<IO*>(sB1hi + sw128_off(t, c)) = hi;
+      *reinterpret_cast<IO*>(sB1lo + sw128_off(t, c)) = lo;
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {       // B2[c][t]
+      const int c = i >> 6, t = i & 63;
+      const float x = (t < p.T && c < C) ? we[c * p.T + t] : 0.f;
+      const __half hi = __float2half_rn(x);
+      const __half lo = __float2half_rn(x - __half2float(hi));
+      *reinterpret_cast<__half*>(sB2hi + sw128_off(c, t)) = hi;
+      *reinterpret_cast<__half*>(sB2lo + sw128_off(c, t)) = lo;
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  constexpr int fmt_io = std::is_same<IO, __nv_bfloat16>::value ? 1 : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer: h tiles =====================
+    if (elect_one()) {
+      for (int it = 0; it < ntile; ++it) {
+        const int s = it % kAttnStages, use = it / kAttnStages;
+        const int tile = blockIdx.x + it * p.ctas_per_sample;
+        mbar_wait(&h_empty[s], (use & 1) ^ 1);
+        mbar_expect_tx(&h_full[s], (uint32_t)stage_bytes);
+        tma_load_2d(sH + s * stage_bytes, &mapH, &h_full[s], tile * 128, b * C);
+        tma_load_2d(sH + s * stage_bytes + box_bytes, &mapH, &h_full[s], tile * 128 + 64, b * C);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);   // A MN-major (pixels contiguous)
+      const uint32_t idesc2 = make_idesc(128, C, 0);                       // P (TMEM) x W.e, fp16
+      const int ks1 = C >> 4, ks2 = NT >> 4;
+      auto gemm1 = [&](int it) {
+        const int s = it % kAttnStages, use = it / kAttnStages, u = it & 1;
+        mbar_wait(&h_full[s], use & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sH + s * stage_bytes);
+        for (int kk = 0; kk < ks1; ++kk) {
+          const uint64_t da = make_desc_sw128_mn_lbo(a0 + kk * 2048, (uint32_t)box_bytes);
+          umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1hi)) + 2 * kk, idesc1, kk ? 1u : 0u);
+          umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1lo)) + 2 * kk, idesc1, 1u);
+        }
+        umma_commit(&h_empty[s]);
+        umma_commit(&s_full[u]);
+      };
+      if (ntile > 0) gemm1(0);
+      if (ntile > 1) gemm1(1);
+      for (int it = 0; it < ntile; ++it) {
+        const int u = it & 1, k = it >> 1;
+        mbar_wait(&p_ready[u], k & 1);
+        mbar_wait(&c_empty[u], (k & 1) ^ 1);
+        tc_fence_after();
+        for (int kk = 0; kk < ks2; ++kk) {
+          umma_f16_ts(tmem + u * bufc + NT, tmem + u * bufc + kk * 8, make_desc_sw128(smem_u32(sB2hi)) + 2 * kk, idesc2,
+                      kk ? 1u : 0u);
+          umma_f16_ts(tmem + u * bufc + NT, tmem + u * bufc + kk * 8, make_desc_sw128(smem_u32(sB2lo)) + 2 * kk, idesc2, 1u);
+        }
+        umma_commit(&c_full[u]);
+        if (it + 2 < ntile) gemm1(it + 2);
+      }
+    }
+  } else {
+    // ===================== epilogue: thread = pixel =====================
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int px = q * 32 + lane;
+    uint64_t valid = 0;
+    for (int t = 0; t < p.T; ++t)
+      if (p.mask[(size_t)b * p.T + t] != 0) valid |= 1ull << t;
+    IO* ctx = (IO*)p.ctx + (size_t)b * p.ctx_bs;
+    IO* attn = p.attn ? (IO*)p.attn + (size_t)b * p.T * p.HW : nullptr;
+
+    auto softmax_phase = [&](int it) {
+      const int u = it & 1, k = it >> 1;
+      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
+      mbar_wait(&s_full[u], k & 1);
+      tc_fence_after();
+      float s[NT];
+      if constexpr (NT == 32) tmem_ld32(tmem + lane_addr + u * bufc, s);
+      else { tmem_ld32(tmem + lane_addr + u * bufc, s); tmem_ld32(tmem + lane_addr + u * bufc + 32, s + 32); }
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (!((valid >> t) & 1)) s[t] = -INFINITY;
+        mx = fmaxf(mx, s[t]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        s[t] = exp2f(s[t] - mx);           // all-masked sample: (-inf) - (-inf) = NaN, like the reference
+        sum += s[t];
+      }
+      const float inv = 1.f / sum;
+      uint32_t pk[NT / 2];
+#pragma unroll
+      for (int t = 0; t < NT; t += 2) {
+        const float a0 = s[t] * inv, a1 = s[t + 1] * inv;
+        s[t] = a0;
+        s[t + 1] = a1;
+        const __half2 h2 = __floats2half2_rn(a0, a1);
+        pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      tmem_st16(tmem + lane_addr + u * bufc, pk);
+      if constexpr (NT == 64) tmem_st16(tmem + lane_addr + u * bufc + 16, pk + 16);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[u]);
+      if (attn != nullptr && pix < p.HW) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          if (t < p.T) attn[(size_t)t * p.HW + pix] = f2h<IO>(s[t]);
+      }
+    };
+    auto context_phase = [&](int it) {
+      const int u = it & 1, k = it >> 1;
+      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
+      mbar_wait(&c_full[u], k & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + lane_addr + u * bufc + NT + c0, v);
+        tmem_ld_wait();
+        if (pix < p.HW) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ctx[(size_t)(c0 + j) * p.HW + pix] = f2h<IO>(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c_empty[u]);
+    };
+    for (int it = 0; it < ntile; ++it) {
+      softmax_phase(it);
+      if (it > 0) context_phase(it - 1);
+    }
+    if (ntile > 0) context_phase(ntile - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+template <typename IO>
+static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaStream_t st) {
+  CUtensorMap mapH;
+  if (int rc = make_tmap_2d(&mapH, images, (uint64_t)p.B * p.C, (uint64_t)p.HW, (uint32_t)p.C,
+                            std::is_same<IO, __nv_bfloat16>::value))
+    return rc;
+  const int NT = p.T <= 32 ? 32 : 64;
+  const int smem = kAttnStages * 2 * p.C * 128 + 2 * NT * 128 + 2 * 64 * 128 + 1024;
+  dim3 grid(p.ctas_per_sample, p.B);
+  const int slot = prof_begin(PROF_ATTN_FWD, st);
+  if (NT == 32) {
+    auto kern = word_attn_fwd_tc_kernel<IO, 32>;
+    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 192, smem, st>>>(mapH, p);
+  } else {
+    auto kern = word_attn_fwd_tc_kernel<IO, 64>;
+    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 192, smem, st>>>(mapH, p);
+  }
+  prof_end(slot, st);
+  return check_launch("word_attn_fwd_tc_kernel");
+}
+
+// 1 when the tensor-core kernel can take this problem
+int word_attn_tc_supported(const void* images, int C, int HW, int T, int io_dtype) {
+  if (io_dtype != AGB_BF16 && io_dtype != AGB_F16) return 0;
+  if (C % 16 != 0 || C < 16 || C > 64 || T > 64 || HW % 8 != 0) return 0;
+  if (((uintptr_t)images & 15) != 0) return 0;
+  return 1;
+}
+
+int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, void* ctx, int64_t ctx_bs, void* attn,
+                     int B, int C, int HW, int T, int io_dtype, float qscale, cudaStream_t st) {
+  AttnFwdParams p;
+  p.we = we; p.mask = mask; p.ctx = ctx; p.attn = attn; p.ctx_bs = ctx_bs;
+  p.B = B; p.C = C; p.HW = HW; p.T = T; p.qscale = qscale;
+  p.tiles = cdiv(HW, 128);
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  p.ctas_per_sample = std::max(1, std::min(p.tiles, cdiv(sms * 4, B)));
+  if (io_dtype == AGB_BF16) return launch_attn_fwd_tc<__nv_bfloat16>(images, p, st);
+  return launch_attn_fwd_tc<__half>(images, p, st);
+}
+
+}  // namespace tc
+}  // namespace agb

@@ -18,6 +18,12 @@ namespace tc {
 int word_attn_tc_supported(const void* images, int C, int HW, int T, int io_dtype);
 int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, void* ctx, int64_t ctx_bs, void* attn,
                      int B, int C, int HW, int T, int io_dtype, float qscale, cudaStream_t st);
+int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dctx_bs, const void* dattn, int C, int HW,
+                               int T, int io_dtype);
+int word_attn_bwd_tc_ctas(int B, int HW);
+int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
+                     void* dimages, float* part, int ctas_per_sample, int B, int C, int HW, int T, int io_dtype,
+                     float scale, cudaStream_t st);
 }  // namespace tc
 
 constexpr int kAttnThreads = 128;
@@ -517,8 +523,7 @@ extern "C" int agb_word_attn_fwd(const void* images, const float* words, int64_t
 
 extern "C" size_t agb_word_attn_bwd_workspace_bytes(int B, int C, int HW, int T) {
   if (B <= 0 || C <= 0 || HW <= 0 || T <= 0 || T > 64) return 0;
-  const int V = bwd_v(pick_tmax(T));
-  const size_t ntiles = cdiv(HW, kAttnThreads * V);
+  const size_t ntiles = cdiv(HW, 128);   // upper bound of the partial sums either kernel family writes
   return ((size_t)B * ntiles + (size_t)B) * C * T * sizeof(float);
 }
 
@@ -539,10 +544,15 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
   const int use_tma = ((C * T) % 4 == 0) && ((uintptr_t)we % 16 == 0);
   const int tm = pick_tmax(T);
   const int V = bwd_v(tm);
-  const int ntiles = cdiv(HW, kAttnThreads * V);
+  int ntiles = cdiv(HW, kAttnThreads * V);
   float* part = (float*)workspace;
-  float* dwe = part + (size_t)B * ntiles * C * T;
   int rc = 0;
+  const bool use_tc = tc::word_attn_bwd_tc_supported(images, dctx, dctx_bs, dattn, C, HW, T, io_dtype) != 0;
+  if (use_tc) ntiles = tc::word_attn_bwd_tc_ctas(B, HW);
+  float* dwe = part + (size_t)B * ntiles * C * T;
+  if (use_tc) {
+    rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dattn, dimages, part, ntiles, B, C, HW, T, io_dtype, scale, st);
+  } else
   AGB_DISPATCH_TMAX(tm, {
     constexpr int VV = TMAX <= 24 ? 2 : 1;
     if (io_dtype == AGB_F32) rc = launch_bwd<float, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);

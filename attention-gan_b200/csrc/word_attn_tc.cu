@@ -285,6 +285,331 @@ static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaSt
   return check_launch("word_attn_fwd_tc_kernel");
 }
 
+// =============================================================================================
+// backward                                                   (autograd of a3)
+//
+//   per tile of 128 pixels (thread = pixel in the epilogues):
+//   GEMM1a  S[px,t] = h^T (W.e) scale log2e          GEMM1b  G[px,t] = dctx^T (W.e)
+//   epilogue 1: a = softmax_t(S), g = G (+ dattn), ds = a (g - sum_t a g);
+//               ds -> TMEM as bf16 hi + lo (A operand of GEMM3); [a | ds] -> smem, transposed
+//               (B operand of GEMM4)
+//   GEMM3   dh[px,c] = sum_t ds[px,t] (W.e)[c,t] scale                        (A from TMEM)
+//   GEMM4   acc[(dctx rows; h rows), (a cols | ds cols)] += [dctx; h][., px] [a | ds][px, .]
+//           accumulated in TMEM over all tiles of the CTA; d(W.e) = acc[dctx, a] + scale acc[h, ds]
+//   epilogue 2: dh -> global
+// TMEM (256 columns): two tile buffers of 96 (S|P, G, dh) + 64 accumulator columns.
+// =============================================================================================
+struct AttnBwdParams {
+  const float* we;
+  const int64_t* mask;
+  const void* dattn;      // [B, T, HW] io dtype or null
+  void* dh;               // [B, C, HW]
+  float* part;            // [B, ctas_per_sample, C, T] per-CTA partial d(W.e)
+  int B, C, HW, T;
+  float scale;
+  int tiles, ctas_per_sample;
+};
+
+constexpr int kBwdNT = 32;
+
+template <typename IO>
+__global__ void __launch_bounds__(192)
+word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapD,
+                        const AttnBwdParams p) {
+  constexpr int NT = kBwdNT;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  const int C = p.C;
+  const int box = C * 128;                       // one [C x 64 px] box
+  const int stage_bytes = 4 * box;               // dctx_lo | h_lo | dctx_hi | h_hi
+  unsigned char* sIn = smem;
+  unsigned char* sB1s = smem + kAttnStages * stage_bytes;      // [t][c] scaled*log2e   hi, lo (io type)
+  unsigned char* sB1u = sB1s + 2 * NT * 128;                   // [t][c] unscaled       hi, lo (io type)
+  unsigned char* sB2 = sB1u + 2 * NT * 128;                    // [c][t] * scale        hi, lo (bf16), 64 rows each
+  unsigned char* sBt = sB2 + 2 * 64 * 128;                     // 2 buffers x 2 px-chunks x [2NT rows][64 px]
+  float* sAcc = reinterpret_cast<float*>(sBt + 2 * 2 * (2 * NT) * 128);   // [2][C][NT]
+  __shared__ uint64_t in_full[kAttnStages], in_empty[kAttnStages], s_full[2], p_ready[2], dh_full[2], dh_empty[2], acc_done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int ntile = (p.tiles - (int)blockIdx.x + p.ctas_per_sample - 1) / p.ctas_per_sample;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kAttnStages; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&in_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&dh_full[i], 1);
+      mbar_init(&dh_empty[i], 4);
+    }
+    mbar_init(&acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  {
+    const float* we = p.we + (size_t)b * C * p.T;
+    const float qs = p.scale * kLog2e;
+    for (int i = threadIdx.x; i < NT * 64; i += blockDim.x) {
+      const int t = i >> 6, c = i & 63;
+      const float w = (t < p.T && c < C) ? we[c * p.T + t] : 0.f;
+      const float xs = w * qs;
+      IO hi = f2h<IO>(xs);
+      *reinterpret_cast<IO*>(sB1s + sw128_off(t, c)) = hi;
+      *reinterpret_cast<IO*>(sB1s + NT * 128 + sw128_off(t, c)) = f2h<IO>(xs - to_f32(hi));
+      hi = f2h<IO>(w);
+      *reinterpret_cast<IO*>(sB1u + sw128_off(t, c)) = hi;
+      *reinterpret_cast<IO*>(sB1u + NT * 128 + sw128_off(t, c)) = f2h<IO>(w - to_f32(hi));
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+      const int c = i >> 6, t = i & 63;
+      const float x = (t < p.T && c < C) ? we[c * p.T + t] * p.scale : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+      *reinterpret_cast<__nv_bfloat16*>(sB2 + sw128_off(c, t)) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(sB2 + 64 * 128 + sw128_off(c, t)) = __float2bfloat16_rn(x - __bfloat162float(hi));
+    }
+    // rows of the transposed [a | ds] operand that no thread writes (t >= T) must be zero
+    for (int i = threadIdx.x; i < 2 * 2 * (2 * NT) * 128 / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(sBt)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  constexpr int fmt_io = std::is_same<IO, __nv_bfloat16>::value ? 1 : 0;
+  constexpr uint32_t kAccCol = 192;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < ntile; ++it) {
+        const int s = it % kAttnStages, use = it / kAttnStages;
+        const int px0 = (blockIdx.x + it * p.ctas_per_sample) * 128;
+        mbar_wait(&in_empty[s], (use & 1) ^ 1);
+        mbar_expect_tx(&in_full[s], (uint32_t)stage_bytes);
+        unsigned char* st = sIn + s * stage_bytes;
+        tma_load_2d(st, &mapD, &in_full[s], px0, b * C);
+        tma_load_2d(st + box, &mapH, &in_full[s], px0, b * C);
+        tma_load_2d(st + 2 * box, &mapD, &in_full[s], px0 + 64, b * C);
+        tma_load_2d(st + 3 * box, &mapH, &in_full[s], px0 + 64, b * C);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);
+      const uint32_t idesc3 = make_idesc(128, C, 1);               // ds (bf16, TMEM) x W.e (bf16)
+      const uint32_t idesc4 = make_idesc(128, 2 * NT, fmt_io);     // [dctx; h] x [a | ds], both K-major over pixels
+      const int ks1 = C >> 4;
+      auto gemm1 = [&](int it) {
+        const int s = it % kAttnStages, use = it / kAttnStages, u = it & 1;
+        mbar_wait(&in_full[s], use & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(sIn + s * stage_bytes);
+        for (int kk = 0; kk < ks1; ++kk) {
+          const uint64_t dh_ = make_desc_sw128_mn_lbo(st + box + kk * 2048, (uint32_t)(2 * box));    // h
+          const uint64_t dd_ = make_desc_sw128_mn_lbo(st + kk * 2048, (uint32_t)(2 * box));          // dctx
+          umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s)) + 2 * kk, idesc1, kk ? 1u : 0u);
+          umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s + NT * 128)) + 2 * kk, idesc1, 1u);
+          umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u)) + 2 * kk, idesc1, kk ? 1u : 0u);
+          umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u + NT * 128)) + 2 * kk, idesc1, 1u);
+        }
+        umma_commit(&s_full[u]);
+      };
+      if (ntile > 0) gemm1(0);
+      if (ntile > 1) gemm1(1);
+      for (int it = 0; it < ntile; ++it) {
+        const int u = it & 1, k = it >> 1, s = it % kAttnStages;
+        mbar_wait(&p_ready[u], k & 1);
+        mbar_wait(&dh_empty[u], (k & 1) ^ 1);
+        tc_fence_after();
+        for (int kk = 0; kk < NT / 16; ++kk) {      // dh = ds (hi + lo) x W.e (hi + lo), lo*lo dropped
+          const uint32_t a_hi = tmem + u * 96 + kk * 8, a_lo = tmem + u * 96 + 16 + kk * 8;
+          const uint64_t b_hi = make_desc_sw128(smem_u32(sB2)) + 2 * kk, b_lo = make_desc_sw128(smem_u32(sB2 + 64 * 128)) + 2 * kk;
+          umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_hi, idesc3, kk ? 1u : 0u);
+          umma_f16_ts(tmem + u * 96 + 2 * NT, a_lo, b_hi, idesc3, 1u);
+          umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_lo, idesc3, 1u);
+        }
+        umma_commit(&dh_full[u]);
+        const uint32_t st = smem_u32(sIn + s * stage_bytes);
+        const uint32_t bt = smem_u32(sBt + u * (2 * (2 * NT) * 128));
+        for (int j = 0; j < 2; ++j)                  // two chunks of 64 pixels
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmem + kAccCol, make_desc_sw128(st + j * 2 * box) + 2 * kk,
+                     make_desc_sw128(bt + j * (2 * NT) * 128) + 2 * kk, idesc4, (it | j | kk) ? 1u : 0u);
+        umma_commit(&in_empty[s]);
+        if (it + 2 < ntile) gemm1(it + 2);
+      }
+      umma_commit(&acc_done);
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int px = q * 32 + lane;
+    uint64_t valid = 0;
+    for (int t = 0; t < p.T; ++t)
+      if (p.mask[(size_t)b * p.T + t] != 0) valid |= 1ull << t;
+    IO* dh = (IO*)p.dh + (size_t)b * C * p.HW;
+    const IO* dattn = p.dattn ? (const IO*)p.dattn + (size_t)b * p.T * p.HW : nullptr;
+
+    auto softmax_phase = [&](int it) {
+      const int u = it & 1, k = it >> 1;
+      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
+      mbar_wait(&s_full[u], k & 1);
+      tc_fence_after();
+      float s[NT], g[NT];
+      tmem_ld32(tmem + lane_addr + u * 96, s);
+      tmem_ld32(tmem + lane_addr + u * 96 + NT, g);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (!((valid >> t) & 1)) s[t] = -INFINITY;
+        mx = fmaxf(mx, s[t]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        s[t] = exp2f(s[t] - mx);
+        sum += s[t];
+      }
+      const float inv = 1.f / sum;
+      float dot = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        s[t] *= inv;
+        if (dattn != nullptr && t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)t * p.HW + pix]);
+        if (t >= p.T) g[t] = 0.f;
+        dot = fmaf(s[t], g[t], dot);
+      }
+      uint32_t pk[NT];                               // [0,16): ds hi pairs, [16,32): ds lo pairs (bf16)
+      unsigned char* btu = sBt + u * (2 * (2 * NT) * 128) + (px >> 6) * ((2 * NT) * 128);
+      const int pc = px & 63;
+      const bool live = pix < p.HW;                  // pixels past the end of the map contribute nothing
+#pragma unroll
+      for (int t = 0; t < NT; t += 2) {
+        float d0 = s[t] * (g[t] - dot), d1 = s[t + 1] * (g[t + 1] - dot);
+        if (!live) { d0 = 0.f; d1 = 0.f; }
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(d0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(d1 - __bfloat162float(h1));
+        pk[t / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        pk[16 + t / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        if (t < p.T) {
+          *reinterpret_cast<IO*>(btu + sw128_off(t, pc)) = f2h<IO>(live ? s[t] : 0.f);
+          *reinterpret_cast<IO*>(btu + sw128_off(NT + t, pc)) = f2h<IO>(d0);
+        }
+        if (t + 1 < p.T) {
+          *reinterpret_cast<IO*>(btu + sw128_off(t + 1, pc)) = f2h<IO>(live ? s[t + 1] : 0.f);
+          *reinterpret_cast<IO*>(btu + sw128_off(NT + t + 1, pc)) = f2h<IO>(d1);
+        }
+      }
+      tmem_st16(tmem + lane_addr + u * 96, pk);
+      tmem_st16(tmem + lane_addr + u * 96 + 16, pk + 16);
+      tmem_st_wait();
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[u]);
+    };
+    auto dh_phase = [&](int it) {
+      const int u = it & 1, k = it >> 1;
+      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
+      mbar_wait(&dh_full[u], k & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < C; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + lane_addr + u * 96 + 2 * NT + c0, v);
+        tmem_ld_wait();
+        if (pix < p.HW) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dh[(size_t)(c0 + j) * p.HW + pix] = f2h<IO>(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dh_empty[u]);
+    };
+    for (int it = 0; it < ntile; ++it) {
+      softmax_phase(it);
+      if (it > 0) dh_phase(it - 1);
+    }
+    if (ntile > 0) dh_phase(ntile - 1);
+    // ---- d(W.e) partial of this CTA ----
+    float* part = p.part + ((size_t)b * p.ctas_per_sample + blockIdx.x) * C * p.T;
+    if (ntile > 0) {
+      mbar_wait(&acc_done, 0);
+      tc_fence_after();
+      float v[2 * NT];
+      tmem_ld32(tmem + lane_addr + kAccCol, v);
+      tmem_ld32(tmem + lane_addr + kAccCol + 32, v + 32);
+      tmem_ld_wait();
+      if (px < C) {
+        for (int t = 0; t < NT; ++t) sAcc[px * NT + t] = v[t];                       // rows of dctx x columns of a
+      } else if (px < 2 * C) {
+        for (int t = 0; t < NT; ++t) sAcc[C * NT + (px - C) * NT + t] = v[NT + t];   // rows of h x columns of ds
+      }
+      named_bar_sync(1, 128);
+      for (int i = threadIdx.x - 64; i < C * p.T; i += 128) {
+        const int c = i / p.T, t = i - c * p.T;
+        part[i] = sAcc[c * NT + t] + p.scale * sAcc[C * NT + c * NT + t];
+      }
+    } else {
+      for (int i = threadIdx.x - 64; i < C * p.T; i += 128) part[i] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dctx_bs, const void* dattn, int C, int HW,
+                               int T, int io_dtype) {
+  if (io_dtype != AGB_BF16 && io_dtype != AGB_F16) return 0;
+  if ((C != 16 && C != 32) || T > kBwdNT || HW % 8 != 0) return 0;
+  if (dctx_bs != (int64_t)C * HW) return 0;
+  if ((((uintptr_t)images | (uintptr_t)dctx) & 15) != 0) return 0;
+  return 1;
+}
+
+int word_attn_bwd_tc_ctas(int B, int HW) {
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = cdiv(HW, 128);
+  return std::max(1, std::min(tiles, cdiv(sms * 2, B)));
+}
+
+int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
+                     void* dimages, float* part, int ctas_per_sample, int B, int C, int HW, int T, int io_dtype,
+                     float scale, cudaStream_t st) {
+  const bool bf = io_dtype == AGB_BF16;
+  CUtensorMap mapH, mapD;
+  if (int rc = make_tmap_2d(&mapH, images, (uint64_t)B * C, (uint64_t)HW, (uint32_t)C, bf)) return rc;
+  if (int rc = make_tmap_2d(&mapD, dctx, (uint64_t)B * C, (uint64_t)HW, (uint32_t)C, bf)) return rc;
+  AttnBwdParams p;
+  p.we = we; p.mask = mask; p.dattn = dattn; p.dh = dimages; p.part = part;
+  p.B = B; p.C = C; p.HW = HW; p.T = T; p.scale = scale;
+  p.tiles = cdiv(HW, 128);
+  p.ctas_per_sample = ctas_per_sample;
+  const int NT = kBwdNT;
+  const int smem = kAttnStages * 4 * C * 128 + 4 * NT * 128 + 2 * 64 * 128 + 2 * 2 * (2 * NT) * 128 + 2 * C * NT * 4 + 1024;
+  dim3 grid(ctas_per_sample, B);
+  const int slot = prof_begin(PROF_ATTN_BWD, st);
+  if (bf) {
+    auto kern = word_attn_bwd_tc_kernel<__nv_bfloat16>;
+    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);
+  } else {
+    auto kern = word_attn_bwd_tc_kernel<__half>;
+    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);
+  }
+  prof_end(slot, st);
+  return check_launch("word_attn_bwd_tc_kernel");
+}
+
 // 1 when the tensor-core kernel can take this problem
 int word_attn_tc_supported(const void* images, int C, int HW, int T, int io_dtype) {
   if (io_dtype != AGB_BF16 && io_dtype != AGB_F16) return 0;

@@ -116,8 +116,10 @@ def test_attention_module_reduced_precision_io(agb, dtype, tol):
     dh, dwords, dW = cf.word_attention_bwd(h64, words.numpy(), weight.reshape(C, E).numpy(), mask.numpy(),
                                            dctx.double().numpy().reshape(B, C, -1), None, True)
     assert_rel(im.grad, dh.reshape(B, C, hw, hw), tol, "dimages")
-    assert_rel(wd.grad, dwords, 1e-3, "dwords")
-    assert_rel(mod.conv1.weight.grad, dW.reshape(C, E, 1, 1), 1e-3, "dweight")
+    # d(W.e) contracts attn / ds over the pixels on the tensor cores in the I/O precision
+    gtol = 5e-3 if dtype == torch.bfloat16 else 1e-3
+    assert_rel(wd.grad, dwords, gtol, "dwords")
+    assert_rel(mod.conv1.weight.grad, dW.reshape(C, E, 1, 1), gtol, "dweight")
 
 
 @pytest.mark.parametrize("T,hw,C", [(1, 5, 4), (64, 9, 32), (33, 8, 64), (18, 3, 1)])

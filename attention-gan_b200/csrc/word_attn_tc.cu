@@ -69,7 +69,22 @@ struct AttnFwdParams {
 
 constexpr int kAttnStages = 3;
 
-template <typename IO, int NT>
+// load TL (multiple of 8, <= 64) consecutive TMEM columns of this thread's lane
+template <int TL>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+  if constexpr (TL >= 32) {
+    tmem_ld32(taddr, v);
+    if constexpr (TL > 32) tmem_ld_cols<TL - 32>(taddr + 32, v + 32);
+  } else if constexpr (TL >= 16) {
+    tmem_ld16(taddr, v);
+    if constexpr (TL > 16) tmem_ld_cols<TL - 16>(taddr + 16, v + 16);
+  } else {
+    tmem_ld8(taddr, v);
+  }
+}
+
+// TL = number of word columns the epilogue touches (T rounded up to 8); NT = MMA N (32 or 64)
+template <typename IO, int NT, int TL>
 __global__ void __launch_bounds__(192)
 word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdParams p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -195,31 +210,35 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
       const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
       mbar_wait(&s_full[u], k & 1);
       tc_fence_after();
-      float s[NT];
-      if constexpr (NT == 32) tmem_ld32(tmem + lane_addr + u * bufc, s);
-      else { tmem_ld32(tmem + lane_addr + u * bufc, s); tmem_ld32(tmem + lane_addr + u * bufc + 32, s + 32); }
+      float s[TL];
+      tmem_ld_cols<TL>(tmem + lane_addr + u * bufc, s);
       tmem_ld_wait();
-      float mx = -INFINITY;
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < TL; ++t) {
         if (!((valid >> t) & 1)) s[t] = -INFINITY;
-        mx = fmaxf(mx, s[t]);
+        m4[t & 3] = fmaxf(m4[t & 3], s[t]);
       }
-      float sum = 0.f;
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < TL; ++t) {
         s[t] = exp2f(s[t] - mx);           // all-masked sample: (-inf) - (-inf) = NaN, like the reference
-        sum += s[t];
+        s4[t & 3] += s[t];
       }
-      const float inv = 1.f / sum;
+      const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
       uint32_t pk[NT / 2];
 #pragma unroll
       for (int t = 0; t < NT; t += 2) {
-        const float a0 = s[t] * inv, a1 = s[t + 1] * inv;
-        s[t] = a0;
-        s[t + 1] = a1;
-        const __half2 h2 = __floats2half2_rn(a0, a1);
-        pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+        if (t < TL) {
+          const float a0 = s[t] * inv, a1 = s[t + 1] * inv;
+          s[t] = a0;
+          s[t + 1] = a1;
+          const __half2 h2 = __floats2half2_rn(a0, a1);
+          pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+        } else {
+          pk[t / 2] = 0u;
+        }
       }
       tmem_st16(tmem + lane_addr + u * bufc, pk);
       if constexpr (NT == 64) tmem_st16(tmem + lane_addr + u * bufc + 16, pk + 16);
@@ -229,7 +248,7 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
       if (lane == 0) mbar_arrive(&p_ready[u]);
       if (attn != nullptr && pix < p.HW) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
+        for (int t = 0; t < TL; ++t)
           if (t < p.T) attn[(size_t)t * p.HW + pix] = f2h<IO>(s[t]);
       }
     };
@@ -272,15 +291,23 @@ static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaSt
   const int smem = kAttnStages * 2 * p.C * 128 + 2 * NT * 128 + 2 * 64 * 128 + 1024;
   dim3 grid(p.ctas_per_sample, p.B);
   const int slot = prof_begin(PROF_ATTN_FWD, st);
-  if (NT == 32) {
-    auto kern = word_attn_fwd_tc_kernel<IO, 32>;
-    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 192, smem, st>>>(mapH, p);
-  } else {
-    auto kern = word_attn_fwd_tc_kernel<IO, 64>;
-    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 192, smem, st>>>(mapH, p);
+#define AGB_ATTN_FWD_CASE(NTV, TLV)                                                              \
+  {                                                                                               \
+    auto kern = word_attn_fwd_tc_kernel<IO, NTV, TLV>;                                            \
+    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+    kern<<<grid, 192, smem, st>>>(mapH, p);                                                       \
   }
+  switch ((p.T + 7) / 8) {
+    case 1: AGB_ATTN_FWD_CASE(32, 8) break;
+    case 2: AGB_ATTN_FWD_CASE(32, 16) break;
+    case 3: AGB_ATTN_FWD_CASE(32, 24) break;
+    case 4: AGB_ATTN_FWD_CASE(32, 32) break;
+    case 5: AGB_ATTN_FWD_CASE(64, 40) break;
+    case 6: AGB_ATTN_FWD_CASE(64, 48) break;
+    case 7: AGB_ATTN_FWD_CASE(64, 56) break;
+    default: AGB_ATTN_FWD_CASE(64, 64) break;
+  }
+#undef AGB_ATTN_FWD_CASE
   prof_end(slot, st);
   return check_launch("word_attn_fwd_tc_kernel");
 }
@@ -312,7 +339,9 @@ struct AttnBwdParams {
 
 constexpr int kBwdNT = 32;
 
-template <typename IO>
+constexpr int kBwdStages = 2;
+
+template <typename IO, int TL>
 __global__ void __launch_bounds__(192)
 word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapD,
                         const AttnBwdParams p) {
@@ -323,12 +352,12 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   const int box = C * 128;                       // one [C x 64 px] box
   const int stage_bytes = 4 * box;               // dctx_lo | h_lo | dctx_hi | h_hi
   unsigned char* sIn = smem;
-  unsigned char* sB1s = smem + kAttnStages * stage_bytes;      // [t][c] scaled*log2e   hi, lo (io type)
+  unsigned char* sB1s = smem + kBwdStages * stage_bytes;       // [t][c] scaled*log2e   hi, lo (io type)
   unsigned char* sB1u = sB1s + 2 * NT * 128;                   // [t][c] unscaled       hi, lo (io type)
-  unsigned char* sB2 = sB1u + 2 * NT * 128;                    // [c][t] * scale        hi, lo (bf16), 64 rows each
-  unsigned char* sBt = sB2 + 2 * 64 * 128;                     // 2 buffers x 2 px-chunks x [2NT rows][64 px]
+  unsigned char* sB2 = sB1u + 2 * NT * 128;                    // [c][t] * scale        hi, lo (bf16), 32 rows each
+  unsigned char* sBt = sB2 + 2 * 32 * 128;                     // 2 buffers x 2 px-chunks x [2NT rows][64 px]
   float* sAcc = reinterpret_cast<float*>(sBt + 2 * 2 * (2 * NT) * 128);   // [2][C][NT]
-  __shared__ uint64_t in_full[kAttnStages], in_empty[kAttnStages], s_full[2], p_ready[2], dh_full[2], dh_empty[2], acc_done;
+  __shared__ uint64_t in_full[kBwdStages], in_empty[kBwdStages], s_full[2], p_ready[2], dh_full[2], dh_empty[2], acc_done;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,7 +365,7 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   const int ntile = (p.tiles - (int)blockIdx.x + p.ctas_per_sample - 1) / p.ctas_per_sample;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kAttnStages; ++i) {
+    for (int i = 0; i < kBwdStages; ++i) {
       mbar_init(&in_full[i], 1);
       mbar_init(&in_empty[i], 1);
     }
@@ -364,12 +393,12 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       *reinterpret_cast<IO*>(sB1u + sw128_off(t, c)) = hi;
       *reinterpret_cast<IO*>(sB1u + NT * 128 + sw128_off(t, c)) = f2h<IO>(w - to_f32(hi));
     }
-    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
       const int c = i >> 6, t = i & 63;
       const float x = (t < p.T && c < C) ? we[c * p.T + t] * p.scale : 0.f;
       const __nv_bfloat16 hi = __float2bfloat16_rn(x);
       *reinterpret_cast<__nv_bfloat16*>(sB2 + sw128_off(c, t)) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(sB2 + 64 * 128 + sw128_off(c, t)) = __float2bfloat16_rn(x - __bfloat162float(hi));
+      *reinterpret_cast<__nv_bfloat16*>(sB2 + 32 * 128 + sw128_off(c, t)) = __float2bfloat16_rn(x - __bfloat162float(hi));
     }
     // rows of the transposed [a | ds] operand that no thread writes (t >= T) must be zero
     for (int i = threadIdx.x; i < 2 * 2 * (2 * NT) * 128 / 16; i += blockDim.x)
@@ -386,7 +415,7 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   if (warp == 0) {
     if (elect_one()) {
       for (int it = 0; it < ntile; ++it) {
-        const int s = it % kAttnStages, use = it / kAttnStages;
+        const int s = it % kBwdStages, use = it / kBwdStages;
         const int px0 = (blockIdx.x + it * p.ctas_per_sample) * 128;
         mbar_wait(&in_empty[s], (use & 1) ^ 1);
         mbar_expect_tx(&in_full[s], (uint32_t)stage_bytes);
@@ -404,7 +433,7 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       const uint32_t idesc4 = make_idesc(128, 2 * NT, fmt_io);     // [dctx; h] x [a | ds], both K-major over pixels
       const int ks1 = C >> 4;
       auto gemm1 = [&](int it) {
-        const int s = it % kAttnStages, use = it / kAttnStages, u = it & 1;
+        const int s = it % kBwdStages, use = it / kBwdStages, u = it & 1;
         mbar_wait(&in_full[s], use & 1);
         tc_fence_after();
         const uint32_t st = smem_u32(sIn + s * stage_bytes);
@@ -421,13 +450,13 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       if (ntile > 0) gemm1(0);
       if (ntile > 1) gemm1(1);
       for (int it = 0; it < ntile; ++it) {
-        const int u = it & 1, k = it >> 1, s = it % kAttnStages;
+        const int u = it & 1, k = it >> 1, s = it % kBwdStages;
         mbar_wait(&p_ready[u], k & 1);
         mbar_wait(&dh_empty[u], (k & 1) ^ 1);
         tc_fence_after();
         for (int kk = 0; kk < NT / 16; ++kk) {      // dh = ds (hi + lo) x W.e (hi + lo), lo*lo dropped
           const uint32_t a_hi = tmem + u * 96 + kk * 8, a_lo = tmem + u * 96 + 16 + kk * 8;
-          const uint64_t b_hi = make_desc_sw128(smem_u32(sB2)) + 2 * kk, b_lo = make_desc_sw128(smem_u32(sB2 + 64 * 128)) + 2 * kk;
+          const uint64_t b_hi = make_desc_sw128(smem_u32(sB2)) + 2 * kk, b_lo = make_desc_sw128(smem_u32(sB2 + 32 * 128)) + 2 * kk;
           umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_hi, idesc3, kk ? 1u : 0u);
           umma_f16_ts(tmem + u * 96 + 2 * NT, a_lo, b_hi, idesc3, 1u);
           umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_lo, idesc3, 1u);
@@ -459,50 +488,57 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
       mbar_wait(&s_full[u], k & 1);
       tc_fence_after();
-      float s[NT], g[NT];
-      tmem_ld32(tmem + lane_addr + u * 96, s);
-      tmem_ld32(tmem + lane_addr + u * 96 + NT, g);
+      float s[TL], g[TL];
+      tmem_ld_cols<TL>(tmem + lane_addr + u * 96, s);
+      tmem_ld_cols<TL>(tmem + lane_addr + u * 96 + NT, g);
       tmem_ld_wait();
-      float mx = -INFINITY;
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < TL; ++t) {
         if (!((valid >> t) & 1)) s[t] = -INFINITY;
-        mx = fmaxf(mx, s[t]);
+        m4[t & 3] = fmaxf(m4[t & 3], s[t]);
       }
-      float sum = 0.f;
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < TL; ++t) {
         s[t] = exp2f(s[t] - mx);
-        sum += s[t];
+        s4[t & 3] += s[t];
       }
-      const float inv = 1.f / sum;
-      float dot = 0.f;
+      const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < TL; ++t) {
         s[t] *= inv;
         if (dattn != nullptr && t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)t * p.HW + pix]);
         if (t >= p.T) g[t] = 0.f;
-        dot = fmaf(s[t], g[t], dot);
+        d4[t & 3] = fmaf(s[t], g[t], d4[t & 3]);
       }
+      const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
       uint32_t pk[NT];                               // [0,16): ds hi pairs, [16,32): ds lo pairs (bf16)
       unsigned char* btu = sBt + u * (2 * (2 * NT) * 128) + (px >> 6) * ((2 * NT) * 128);
       const int pc = px & 63;
       const bool live = pix < p.HW;                  // pixels past the end of the map contribute nothing
 #pragma unroll
       for (int t = 0; t < NT; t += 2) {
-        float d0 = s[t] * (g[t] - dot), d1 = s[t + 1] * (g[t + 1] - dot);
-        if (!live) { d0 = 0.f; d1 = 0.f; }
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(d0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(d1 - __bfloat162float(h1));
-        pk[t / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        pk[16 + t / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        if (t < p.T) {
-          *reinterpret_cast<IO*>(btu + sw128_off(t, pc)) = f2h<IO>(live ? s[t] : 0.f);
-          *reinterpret_cast<IO*>(btu + sw128_off(NT + t, pc)) = f2h<IO>(d0);
-        }
-        if (t + 1 < p.T) {
-          *reinterpret_cast<IO*>(btu + sw128_off(t + 1, pc)) = f2h<IO>(live ? s[t + 1] : 0.f);
-          *reinterpret_cast<IO*>(btu + sw128_off(NT + t + 1, pc)) = f2h<IO>(d1);
+        if (t < TL) {
+          float d0 = s[t] * (g[t] - dot), d1 = s[t + 1] * (g[t + 1] - dot);
+          if (!live) { d0 = 0.f; d1 = 0.f; }
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(d0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(d1 - __bfloat162float(h1));
+          pk[t / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          pk[16 + t / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          if (t < p.T) {
+            *reinterpret_cast<IO*>(btu + sw128_off(t, pc)) = f2h<IO>(live ? s[t] : 0.f);
+            *reinterpret_cast<IO*>(btu + sw128_off(NT + t, pc)) = f2h<IO>(d0);
+          }
+          if (t + 1 < p.T) {
+            *reinterpret_cast<IO*>(btu + sw128_off(t + 1, pc)) = f2h<IO>(live ? s[t + 1] : 0.f);
+            *reinterpret_cast<IO*>(btu + sw128_off(NT + t + 1, pc)) = f2h<IO>(d1);
+          }
+        } else {
+          pk[t / 2] = 0u;
+          pk[16 + t / 2] = 0u;
         }
       }
       tmem_st16(tmem + lane_addr + u * 96, pk);
@@ -578,7 +614,7 @@ int word_attn_bwd_tc_ctas(int B, int HW) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = cdiv(HW, 128);
-  return std::max(1, std::min(tiles, cdiv(sms * 2, B)));
+  return std::max(1, std::min(cdiv(tiles, 2), std::max(1, (sms * 2) / B)));
 }
 
 int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
@@ -594,18 +630,26 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
   p.tiles = cdiv(HW, 128);
   p.ctas_per_sample = ctas_per_sample;
   const int NT = kBwdNT;
-  const int smem = kAttnStages * 4 * C * 128 + 4 * NT * 128 + 2 * 64 * 128 + 2 * 2 * (2 * NT) * 128 + 2 * C * NT * 4 + 1024;
+  const int smem = kBwdStages * 4 * C * 128 + 4 * NT * 128 + 2 * 32 * 128 + 2 * 2 * (2 * NT) * 128 + 2 * C * NT * 4 + 1024;
   dim3 grid(ctas_per_sample, B);
   const int slot = prof_begin(PROF_ATTN_BWD, st);
-  if (bf) {
-    auto kern = word_attn_bwd_tc_kernel<__nv_bfloat16>;
-    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);
-  } else {
-    auto kern = word_attn_bwd_tc_kernel<__half>;
-    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);
+#define AGB_ATTN_BWD_CASE(TLV)                                                                    \
+  if (bf) {                                                                                       \
+    auto kern = word_attn_bwd_tc_kernel<__nv_bfloat16, TLV>;                                      \
+    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);                                                 \
+  } else {                                                                                        \
+    auto kern = word_attn_bwd_tc_kernel<__half, TLV>;                                             \
+    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);                                                 \
   }
+  switch ((T + 7) / 8) {
+    case 1: AGB_ATTN_BWD_CASE(8) break;
+    case 2: AGB_ATTN_BWD_CASE(16) break;
+    case 3: AGB_ATTN_BWD_CASE(24) break;
+    default: AGB_ATTN_BWD_CASE(32) break;
+  }
+#undef AGB_ATTN_BWD_CASE
   prof_end(slot, st);
   return check_launch("word_attn_bwd_tc_kernel");
 }
@@ -630,7 +674,8 @@ int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, v
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  p.ctas_per_sample = std::max(1, std::min(p.tiles, cdiv(sms * 4, B)));
+  // whole waves of resident CTAs (3 per SM by registers / shared memory), at least 2 tiles each
+  p.ctas_per_sample = std::max(1, std::min(cdiv(p.tiles, 2), std::max(1, (sms * 3) / B)));
   if (io_dtype == AGB_BF16) return launch_attn_fwd_tc<__nv_bfloat16>(images, p, st);
   return launch_attn_fwd_tc<__half>(images, p, st);
 }

@@ -30,7 +30,7 @@ SIGNATURES = {
     "agb_word_attn_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),
-    "agb_word_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "agb_word_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "agb_word_attn_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

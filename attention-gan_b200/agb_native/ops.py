@@ -77,7 +77,7 @@ def word_attn_bwd(images, words, weight, mask, we, dctx, dattn, scaled: bool, ne
     dimages = torch.empty_like(images)
     dwords = torch.empty((B, E, T), dtype=torch.float32, device=images.device) if need_dwords else None
     dweight = torch.empty((C, E), dtype=torch.float32, device=images.device) if need_dweight else None
-    nbytes = N.lib().agb_word_attn_bwd_workspace_bytes(B, C, HW, T)
+    nbytes = N.lib().agb_word_attn_bwd_workspace_bytes(B, C, HW, E, T)
     ws = _ws(nbytes, images.device)
     rc = N.lib().agb_word_attn_bwd(_p(images), _p(words), words.stride(0), words.stride(1), words.stride(2),
                                    _p(weight), _p(mask), _p(we), _p(dctx), dctx.stride(0), _p(dattn),

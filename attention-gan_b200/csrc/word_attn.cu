@@ -399,6 +399,17 @@ __global__ void word_attn_bwd_reduce_kernel(const float* __restrict__ part, int 
   }
 }
 
+// dwe[b,i] = sum over the per-CTA partials (fixed order -> deterministic)
+__global__ void sum_partials_kernel(const float* __restrict__ part, int nparts, int64_t part_stride,
+                                    int64_t batch_stride, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  const float* p = part + (int64_t)b * batch_stride + i;
+  float acc = 0.f;
+  for (int k = 0; k < nparts; ++k) acc += p[(int64_t)k * part_stride];
+  out[(size_t)b * n + i] = acc;
+}
+
 // backward, kernel 3: dW[c,e] = sum_b sum_t dwe[b,c,t] * words[b,e,t]   (autograd of conv1, weight side)
 __global__ void word_attn_bwd_dw_kernel(const float* __restrict__ dwe, const float* __restrict__ words,
                                         int64_t ws_b, int64_t ws_e, int64_t ws_t,
@@ -502,8 +513,14 @@ extern "C" int agb_word_attn_fwd(const void* images, const float* words, int64_t
   if (int rc = check_common(B, C, HW, E, T, io_dtype)) return rc;
   if (!images || !words || !conv_w || !mask || !ctx || !we) return fail_arg("null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  word_proj_fwd_kernel<<<B, 256, 0, st>>>(words, ws_b, ws_e, ws_t, conv_w, we, C, E, T);
-  if (int rc = check_launch("word_proj_fwd_kernel")) return rc;
+  {  // we[b][c,t] = sum_e W[c,e] words[b][e,t]                     (attention.py:50-52, conv1 1x1)
+    SgemmArgs g{};
+    g.A = conv_w; g.a_m = E; g.a_k = 1; g.a_batch = 0;
+    g.B = words; g.b_k = ws_e; g.b_n = ws_t; g.b_batch = ws_b;
+    g.C = we; g.c_m = T; g.c_n = 1; g.c_batch = (int64_t)C * T;
+    g.M = C; g.N = T; g.K = E; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
+    if (int rc = sgemm_strided(g, B, st)) return rc;
+  }
   const float qscale = (scaled ? 1.f / sqrtf((float)C) : 1.f) * kLog2e;
   // 16-bit feature maps: both contractions on tcgen05 (word_attn_tc.cu); fp32 maps and odd shapes:
   // CUDA cores.  Both are native sm_100a kernels of this library.
@@ -521,10 +538,17 @@ extern "C" int agb_word_attn_fwd(const void* images, const float* words, int64_t
   return rc;
 }
 
-extern "C" size_t agb_word_attn_bwd_workspace_bytes(int B, int C, int HW, int T) {
-  if (B <= 0 || C <= 0 || HW <= 0 || T <= 0 || T > 64) return 0;
+static int dw_splits(int B) {
+  int s = 1;
+  for (int k = 2; k <= 32 && k <= B; ++k)
+    if (B % k == 0) s = k;
+  return s;
+}
+
+extern "C" size_t agb_word_attn_bwd_workspace_bytes(int B, int C, int HW, int E, int T) {
+  if (B <= 0 || C <= 0 || HW <= 0 || E <= 0 || T <= 0 || T > 64) return 0;
   const size_t ntiles = cdiv(HW, 128);   // upper bound of the partial sums either kernel family writes
-  return ((size_t)B * ntiles + (size_t)B) * C * T * sizeof(float);
+  return (((size_t)B * ntiles + (size_t)B) * C * T + (size_t)dw_splits(B) * C * E) * sizeof(float);
 }
 
 extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t ws_b, int64_t ws_e,
@@ -535,8 +559,8 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
                                  int io_dtype, int scaled, void* stream) {
   if (int rc = check_common(B, C, HW, E, T, io_dtype)) return rc;
   if (!images || !words || !conv_w || !mask || !we || !dctx || !dimages || !workspace) return fail_arg("null pointer");
-  if (workspace_bytes < agb_word_attn_bwd_workspace_bytes(B, C, HW, T)) {
-    set_error("workspace too small: %zu < %zu", workspace_bytes, agb_word_attn_bwd_workspace_bytes(B, C, HW, T));
+  if (workspace_bytes < agb_word_attn_bwd_workspace_bytes(B, C, HW, E, T)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, agb_word_attn_bwd_workspace_bytes(B, C, HW, E, T));
     return AGB_E_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -560,11 +584,29 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
     else rc = launch_bwd<__half, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
   });
   if (rc) return rc;
-  word_attn_bwd_reduce_kernel<<<B, 256, (size_t)C * T * sizeof(float), st>>>(part, ntiles, conv_w, dwe, dwords, C, E, T);
-  if ((rc = check_launch("word_attn_bwd_reduce_kernel"))) return rc;
+  // dwe[b] = sum of the partials; dwords[b][e,t] = sum_c W[c,e] dwe[b][c,t]; dW[c,e] = sum_b,t dwe[b][c,t] words[b][e,t]
+  sum_partials_kernel<<<dim3(cdiv(C * T, 128), B), 128, 0, st>>>(part, ntiles, (int64_t)C * T, (int64_t)ntiles * C * T,
+                                                                 C * T, dwe);
+  if ((rc = check_launch("sum_partials_kernel"))) return rc;
+  if (dwords) {
+    SgemmArgs g{};
+    g.A = conv_w; g.a_m = 1; g.a_k = E; g.a_batch = 0;
+    g.B = dwe; g.b_k = T; g.b_n = 1; g.b_batch = (int64_t)C * T;
+    g.C = dwords; g.c_m = T; g.c_n = 1; g.c_batch = (int64_t)E * T;
+    g.M = E; g.N = T; g.K = C; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
+    if ((rc = sgemm_strided(g, B, st))) return rc;
+  }
   if (dconv_w) {
-    word_attn_bwd_dw_kernel<<<cdiv(C * E, 128), 128, 0, st>>>(dwe, words, ws_b, ws_e, ws_t, dconv_w, B, C, E, T);
-    if ((rc = check_launch("word_attn_bwd_dw_kernel"))) return rc;
+    const int S = dw_splits(B), per = B / S;
+    float* dwp = dwe + (size_t)B * C * T;
+    SgemmArgs g{};
+    g.A = dwe; g.a_m = T; g.a_k = 1; g.a_kb = (int64_t)C * T; g.a_batch = (int64_t)per * C * T;
+    g.B = words; g.b_k = ws_t; g.b_n = ws_e; g.b_kb = ws_b; g.b_batch = (int64_t)per * ws_b;
+    g.C = dwp; g.c_m = E; g.c_n = 1; g.c_batch = (int64_t)C * E;
+    g.M = C; g.N = E; g.K = T; g.KB = per; g.alpha = 1.f; g.accumulate = 0;
+    if ((rc = sgemm_strided(g, S, st))) return rc;
+    sum_partials_kernel<<<dim3(cdiv(C * E, 128), 1), 128, 0, st>>>(dwp, S, (int64_t)C * E, 0, C * E, dconv_w);
+    if ((rc = check_launch("sum_partials_kernel"))) return rc;
   }
   return 0;
 }

@@ -287,9 +287,9 @@ def run_native(args):
         with torch.no_grad():
             mod.conv1.weight.copy_(weight.to(dev))
         mod.apply_mask(mask_d)
-        out_h = torch.empty(1, dtype=torch.float32).pin_memory()
+        out_h = torch.empty(256, dtype=tdt).pin_memory()
         h2d = sum(t.numel() * t.element_size() for t in (img_h, dctx_h, wrd_h))
-        d2h = 4
+        d2h = out_h.numel() * out_h.element_size()
 
         def make_dev():
             return [img_h.to(dev).requires_grad_(True), wrd_h.to(dev).requires_grad_(True), dctx_h.to(dev)]
@@ -310,7 +310,7 @@ def run_native(args):
             mod.conv1.weight.grad = None
             ctx, attn = mod(im, wd.transpose(1, 2))
             ctx.backward(dctx)
-            out_h.copy_(im.grad.float().abs().max().reshape(1), non_blocking=True)   # the step's metric
+            out_h.copy_(im.grad.reshape(-1)[:256], non_blocking=True)   # read a slice of the step's result back
 
         units = Bl * hw * hw
         total_units = B * hw * hw

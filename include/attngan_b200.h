@@ -97,7 +97,7 @@ int agb_word_attn_fwd(const void* images, const float* words, int64_t ws_b, int6
                       int io_dtype, int scaled, void* stream);
 
 /* bytes of scratch agb_word_attn_bwd needs (per-tile partial sums of d(W.e)) */
-size_t agb_word_attn_bwd_workspace_bytes(int B, int C, int HW, int T);
+size_t agb_word_attn_bwd_workspace_bytes(int B, int C, int HW, int E, int T);
 
 /* replaces autograd of AttentionModule.forward
  *   dctx    [B,C,HW] io dtype, batch stride dctx_bs;  dattn [B,T,HW] io dtype or NULL

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     assert lib.agb_damsm_supported(18, 256, 289, pkg.native.AGB_MATH_FP32) == 1
     assert lib.agb_damsm_supported(65, 256, 289, pkg.native.AGB_MATH_FP32) == 0
     assert lib.agb_damsm_workspace_bytes(48, 48, 18, 256, 289, 0) > 0
-    assert lib.agb_word_attn_bwd_workspace_bytes(2, 32, 4096, 18) > 0
+    assert lib.agb_word_attn_bwd_workspace_bytes(2, 32, 4096, 256, 18) > 0
 
 
 def test_argument_errors_are_reported_without_a_gpu():

@@ -412,6 +412,8 @@ damsm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+#include "damsm_tc_fwd2.inc"
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -511,19 +513,19 @@ static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t w
   CUtensorMap mapW, mapCt, mapCk;
   if (int rc = make_tmap_2d(&mapW, pk.Wh, (uint64_t)pl.nt_max * kTileN, kD, 128, bf)) return rc;
   if (int rc = make_tmap_2d(&mapCt, pk.Ct, (uint64_t)Bi * kRRows, kD, 128, bf)) return rc;
-  if (int rc = make_tmap_2d(&mapCk, pk.Ck, (uint64_t)Bi * kD, kRCols, 256, bf)) return rc;
+  if (int rc = make_tmap_2d(&mapCk, pk.Ck, (uint64_t)Bi * kD, kRCols, 128, bf)) return rc;
   FwdParams p;
   p.tile_first = pk.tfirst; p.tile_ncap = pk.tncap; p.ntiles = pk.ntiles; p.cap_row = pk.cap_row; p.cap_lens = cap_lens;
   p.pn = pk.pn; p.m_out = m_out; p.Bi = Bi; p.Bc = Bc; p.T = T; p.R = R;
   p.scale_log2 = kLog2e / sqrtf((float)kD);
   p.g1_log2 = gamma1 * kLog2e;
   p.gamma2 = gamma2;
-  auto kern = damsm_fwd_kernel<T16>;
-  AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  auto kern = damsm_fwd2_kernel<T16>;
+  AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
   const long long max_items = (long long)Bi * pl.nt_max;
   const int grid = (int)std::min<long long>(num_sms(), max_items);
   const int slot = prof_begin(PROF_DAMSM_TC_FWD, st);
-  kern<<<grid, kThreads, kSmemBytes, st>>>(mapW, mapCt, mapCk, p);
+  kern<<<grid, kThreads, kSmemBytes2, st>>>(mapW, mapCt, mapCk, p);
   prof_end(slot, st);
   return check_launch("damsm_fwd_kernel");
 }

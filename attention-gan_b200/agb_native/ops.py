@@ -119,7 +119,7 @@ def damsm_fwd(img: torch.Tensor, words: torch.Tensor, cap_lens: torch.Tensor, ga
 
 
 def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords: bool,
-              math: int = N.AGB_MATH_FP32):
+              math: int = N.AGB_MATH_FP32, m_fwd: Optional[torch.Tensor] = None):
     """dm [Bi,Bc] = dLoss/dm, gscale: device scalar or None.
     Returns (dimg [Bi,D,R], dwords [Bc,T,D] word-major or None)."""
     require_cuda(img, words, cap_lens, dm, gscale)
@@ -130,7 +130,7 @@ def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords
     dwords = torch.empty((Bc, T, D), dtype=torch.float32, device=dev) if need_dwords else None
     ws = _ws(N.lib().agb_damsm_workspace_bytes(Bi, Bc, T, D, R, math), dev)
     rc = N.lib().agb_damsm_bwd(_p(img), _p(words), words.stride(0), words.stride(1), words.stride(2),
-                               _p(cap_lens), Bi, Bc, T, D, R, gamma1, gamma2, eps, _p(dm), _p(gscale),
+                               _p(cap_lens), Bi, Bc, T, D, R, gamma1, gamma2, eps, _p(dm), _p(m_fwd), _p(gscale),
                                _p(dimg), _p(dwords), _p(ws), ws.numel(), math, _stream(img))
     N.check(rc, "agb_damsm_bwd")
     return dimg, dwords

@@ -21,6 +21,8 @@
 //   Wh [tiles*128, 256]   packed caption words, K-major rows; unused rows are zero
 //   Ct [Bi*384, 256]      regions as rows (M operand of GEMM1), rows >= R zero
 //   Ck [Bi*256, 320]      features as rows (N operand of GEMM2), columns >= R zero
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -81,7 +83,9 @@ __global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, i
     if (threadIdx.x == 0) {
       for (int k = 0; k < n; ++k) {
         const int i = base + k, L = lens_s[k];
-        if (row + L > kTileN || i - first == 128) {
+        // the epilogues read a caption's TMEM columns in windows of 8: keep the whole window inside the
+        // tile (the last accumulator buffer ends at TMEM column 512)
+        if (row + ((L + 7) & ~7) > kTileN || i - first == 128) {
           tile_first[tile] = first;
           tile_ncap[tile] = i - first;
           ++tile;
@@ -423,12 +427,12 @@ struct TcPlan {
   // staged backward, per chunk of ct tiles (N = ct*128 word rows) and all Bi images
   int ct;        // tiles per chunk
   int splits;    // slices of the image range in the dW GEMM
-  size_t off_S32, off_E16, off_V32, off_dV16, off_G32, off_DS16, off_A116, off_stat, off_dwp, total;
+  size_t off_S32, off_E16, off_V32, off_dV16, off_G32, off_DS16, off_A116, off_stat, off_dwp, off_m, total;
 };
 
 static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   TcPlan p;
-  const int per_tile = 128 / T;  // captions that always fit in one tile
+  const int per_tile = 128 / ((T + 7) & ~7);  // captions that always fit in one tile (8-column windows)
   p.nt_max = (Bc + per_tile - 1) / per_tile;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 1024); return at; };
@@ -458,6 +462,7 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_A116 = take(rows * kRCols * 2);
   p.off_stat = take(rows * 16);
   p.off_dwp = take((size_t)p.splits * ct * kTileN * kD * 4);
+  p.off_m = take((size_t)Bi * Bc * 4);
   p.total = o;
   return p;
 }
@@ -504,11 +509,21 @@ static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t 
 }
 
 template <typename T16>
+static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1,
+                      float gamma2, float* m_out, const TcPlan& pl, cudaStream_t st);
+
+template <typename T16>
 static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                    const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1, float gamma2, float* m_out,
                    char* ws, const TcPlan& pl, cudaStream_t st) {
   Packed pk;
   if (int rc = run_pack<T16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, ws, pl, &pk, st)) return rc;
+  return launch_fwd<T16>(pk, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, pl, st);
+}
+
+template <typename T16>
+static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1,
+                      float gamma2, float* m_out, const TcPlan& pl, cudaStream_t st) {
   const bool bf = std::is_same<T16, __nv_bfloat16>::value;
   CUtensorMap mapW, mapCt, mapCk;
   if (int rc = make_tmap_2d(&mapW, pk.Wh, (uint64_t)pl.nt_max * kTileN, kD, 128, bf)) return rc;
@@ -531,6 +546,8 @@ static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t w
 }
 
 #include "damsm_tc_bwd.inc"
+#include "damsm_tc_bwd2.inc"
+#include "damsm_tc_bwd2_host.inc"
 
 }  // namespace tc
 
@@ -569,8 +586,8 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
 
 int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
-                 float eps, const float* dm, const float* gscale, float* dimg, float* dwords, void* workspace,
-                 size_t workspace_bytes, int math, cudaStream_t st) {
+                 float eps, const float* dm, const float* m_fwd, const float* gscale, float* dimg, float* dwords,
+                 void* workspace, size_t workspace_bytes, int math, cudaStream_t st) {
   if (Bi <= 0 || Bc <= 0) return fail_arg("non-positive batch");
   if (Bi > 65535) return fail_unsupported("Bi=%d > 65535", Bi);
   const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R);
@@ -578,11 +595,19 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
     set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
     return AGB_E_WORKSPACE;
   }
+  static const bool staged = getenv("AGB_DAMSM_STAGED_BWD") != nullptr;   // round-1 staged backward, kept for A/B runs
+  if (staged) {
+    if (math == AGB_MATH_TC_BF16)
+      return tc::run_bwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale,
+                                        dimg, dwords, (char*)workspace, pl, st);
+    return tc::run_bwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale, dimg,
+                               dwords, (char*)workspace, pl, st);
+  }
   if (math == AGB_MATH_TC_BF16)
-    return tc::run_bwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale,
-                                      dimg, dwords, (char*)workspace, pl, st);
-  return tc::run_bwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale, dimg,
-                             dwords, (char*)workspace, pl, st);
+    return tc::run_bwd2<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd,
+                                       gscale, dimg, dwords, (char*)workspace, pl, st);
+  return tc::run_bwd2<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd, gscale,
+                              dimg, dwords, (char*)workspace, pl, st);
 }
 
 }  // namespace agb

@@ -119,7 +119,7 @@ class _WordsLossFn(torch.autograd.Function):
                                    cfg.math, cnn32 if fuse_sent else None, rnn32 if fuse_sent else None)
         m_all = _gather_cat(m, cfg.group) if ex.W > 1 else m
         loss, dm = o.contrastive(m_all, ex.cls, ex.labels, cfg.gamma3, cfg.lam, ex.row0, Bl)
-        ctx.save_for_backward(img3, w32, dm)
+        ctx.save_for_backward(img3, w32, dm, m)
         ctx.cfg, ctx.ex = cfg, ex
         ctx.meta = (img.shape, img.dtype, words.dtype)
         outs = [loss.reshape(())]
@@ -135,13 +135,13 @@ class _WordsLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dloss, *unused):
-        img3, w32, dm = ctx.saved_tensors
+        img3, w32, dm, m = ctx.saved_tensors
         cfg, ex = ctx.cfg, ctx.ex
         ishape, idt, wdt = ctx.meta
         need_w = ctx.needs_input_grad[1]
         gscale = dloss.detach().float().reshape(1).contiguous()
         dimg, dwords = cfg.ops.damsm_bwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, dm, gscale, need_w,
-                                         cfg.math)
+                                         cfg.math, m)
         if dwords is not None:
             if ex.W > 1:
                 dwords = _reduce_scatter_sum(dwords, cfg.group)

@@ -138,6 +138,8 @@ int agb_damsm_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws
 
 /* replaces autograd of the same loop
  *   dm      [Bi,Bc]  fp32: dLoss/dm (already includes gamma3 and lambda, see agb_contrastive)
+ *   m_fwd   [Bi,Bc]  fp32: m_out of the matching agb_damsm_fwd call, or NULL (then the tensor-core
+ *                    path recomputes it; the fp32 path does not need it)
  *   gscale  device scalar (upstream d/dloss) or NULL for 1
  *   dimg    [Bi,D,R] fp32 out (overwritten)
  *   dwords  [Bc,T,D] fp32 contiguous out (note: word-major, the RNN's physical layout), or NULL
@@ -145,8 +147,9 @@ int agb_damsm_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws
  *           sharded case this is the rank's partial sum over its images. */
 int agb_damsm_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                   const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1,
-                  float gamma2, float eps, const float* dm, const float* gscale, float* dimg,
-                  float* dwords, void* workspace, size_t workspace_bytes, int math, void* stream);
+                  float gamma2, float eps, const float* dm, const float* m_fwd, const float* gscale,
+                  float* dimg, float* dwords, void* workspace, size_t workspace_bytes, int math,
+                  void* stream);
 
 /* returns 1 when (T, D, R, math) is inside the compiled range of the requested path */
 int agb_damsm_supported(int T, int D, int R, int math);

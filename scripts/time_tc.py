@@ -19,8 +19,8 @@ for B in sizes:
     dm = torch.randn(B, B, generator=g).cuda() * 1e-3
     Lbar = lens.float().mean().item()
     for it in range(3):
-        ops.damsm_fwd(img, wrd, lens, 4.0, 5.0, 1e-8, 0, False, math)
-        if bwd: ops.damsm_bwd(img, wrd, lens, 4.0, 5.0, 1e-8, dm, None, True, math)
+        mfw = ops.damsm_fwd(img, wrd, lens, 4.0, 5.0, 1e-8, 0, False, math)[0]
+        if bwd: ops.damsm_bwd(img, wrd, lens, 4.0, 5.0, 1e-8, dm, None, True, math, mfw)
     torch.cuda.synchronize()
     lib.agb_prof_enable(1)
     reps = 5
@@ -31,7 +31,7 @@ for B in sizes:
     e1.record()
     if bwd:
         for it in range(reps):
-            ops.damsm_bwd(img, wrd, lens, 4.0, 5.0, 1e-8, dm, None, True, math)
+            ops.damsm_bwd(img, wrd, lens, 4.0, 5.0, 1e-8, dm, None, True, math, mfw)
     e2.record()
     torch.cuda.synchronize()
     out = {t: read(t) for t in (1, 2, 3)}

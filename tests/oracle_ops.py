@@ -35,7 +35,7 @@ def damsm_fwd(img, words, cap_lens, gamma1, gamma2, eps=1e-8, row_offset=0, want
     return torch.from_numpy(m).float(), att, scos
 
 
-def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords, math=0):
+def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords, math=0, m_fwd=None):
     g = 1.0 if gscale is None else float(gscale.item())
     dc, dw = cf.words_similarity_bwd(_np(img), _np(words), _np(cap_lens), _np(dm).astype(np.float64) * g,
                                      gamma1, gamma2, eps)

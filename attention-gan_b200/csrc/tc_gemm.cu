@@ -19,7 +19,7 @@ namespace tc {
 
 constexpr int kGemmStages = 6;
 constexpr int kGemmStageBytes = 2 * kChunkBytes16;   // A chunk + B chunk, 16 KB each
-constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024;
+constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024;   // >= the 128 x 129 fp32 store tile
 
 // SWIZZLE_128B descriptor for an MN-major operand: tile = [k rows][64 mn elements], 8-row groups
 // 1024 B apart (SBO), successive 64-wide mn blocks `lbo_bytes` apart (LBO)
@@ -124,32 +124,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&done, 0);
       tc_fence_after();
     }
-    const int m = m0 + warp * 32 + lane;
     float* Cz = g.C + (int64_t)z * g.c_z;
-    for (int c0 = 0; c0 < g.NT; c0 += 32) {
-      float v[32];
-      if (total > 0) {
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;       // empty reduction: the sum is zero
-      }
-      if (m < m_valid) {
-        float* prow = Cz + (int64_t)m * g.c_m + (int64_t)(n0 + c0) * g.c_n;
-        if (g.c_n == 1 && n0 + c0 + 32 <= g.N && ((uintptr_t)prow & 15) == 0) {
-          // 32 consecutive fp32 of one output row: eight 16-byte stores per thread
-          float4* p4 = reinterpret_cast<float4*>(prow);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x = make_float4(g.alpha * v[4 * j], g.alpha * v[4 * j + 1], g.alpha * v[4 * j + 2], g.alpha * v[4 * j + 3]);
-            if (g.accumulate) {
-              const float4 o = p4[j];
-              x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
-            }
-            p4[j] = x;
-          }
+    if (g.c_n == 1) {
+      // n-contiguous output: transpose through shared memory (the operand ring is idle now) so that
+      // every warp writes whole rows -- coalesced for any row pitch / alignment
+      float* tile = reinterpret_cast<float*>(smem);          // [128][NT + 1]
+      const int pitch = g.NT + 1;
+      const int row = warp * 32 + lane;
+      for (int c0 = 0; c0 < g.NT; c0 += 32) {
+        float v[32];
+        if (total > 0) {
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+          tmem_ld_wait();
         } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;           // empty reduction: the sum is zero
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tile[row * pitch + c0 + j] = v[j];
+      }
+      named_bar_sync(1, 128);
+      const int rows = min(128, m_valid - m0);
+      const int cols = min(g.NT, g.N - n0);
+      for (int r = warp; r < rows; r += 4) {
+        float* prow = Cz + (int64_t)(m0 + r) * g.c_m + n0;
+        for (int n = lane; n < cols; n += 32) {
+          const float x = g.alpha * tile[r * pitch + n];
+          prow[n] = g.accumulate ? (prow[n] + x) : x;
+        }
+      }
+    } else {
+      const int m = m0 + warp * 32 + lane;
+      for (int c0 = 0; c0 < g.NT; c0 += 32) {
+        float v[32];
+        if (total > 0) {
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (m < m_valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c0 + j;
@@ -183,7 +198,7 @@ int tc_gemm(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap& 
   // short reductions get a short ring so that several CTAs share an SM and hide each other's prologue
   const long long chunks = (long long)g.KB * (g.K / 64);
   g.stages = (int)std::min<long long>(kGemmStages, std::max<long long>(2, chunks));
-  const int smem_bytes = g.stages * (kChunkBytes16 + g.NT * 128) + 1024;
+  const int smem_bytes = std::max(g.stages * (kChunkBytes16 + g.NT * 128), 128 * (g.NT + 1) * 4) + 1024;
   const int slot = prof_begin(PROF_DAMSM_TC_BWD, st);
   tc_gemm_kernel<<<grid, 192, smem_bytes, st>>>(mapA, mapB, g);
   prof_end(slot, st);

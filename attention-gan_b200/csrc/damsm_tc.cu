@@ -21,8 +21,6 @@
 //   Wh [tiles*128, 256]   packed caption words, K-major rows; unused rows are zero
 //   Ct [Bi*384, 256]      regions as rows (M operand of GEMM1), rows >= R zero
 //   Ck [Bi*256, 320]      features as rows (N operand of GEMM2), columns >= R zero
-#include <stdlib.h>
-
 #include <algorithm>
 #include <type_traits>
 
@@ -424,10 +422,10 @@ damsm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant
 struct TcPlan {
   int nt_max;
   size_t off_Wh, off_pn, off_caprow, off_tfirst, off_tncap, off_ntiles, off_Ct, off_Ck, off_attS, off_attB;
-  // staged backward, per chunk of ct tiles (N = ct*128 word rows) and all Bi images
+  // fused backward staging, per chunk of ct word tiles (N = ct*128 word rows) and all Bi images
   int ct;        // tiles per chunk
-  int splits;    // slices of the image range in the dW GEMM
-  size_t off_S32, off_E16, off_V32, off_dV16, off_G32, off_DS16, off_A116, off_stat, off_dwp, off_m, total;
+  int splits;    // slices of the image range in the d words GEMM
+  size_t off_E16, off_dV16, off_DS16, off_A116, off_dpp, off_dwp, off_m, total;
 };
 
 static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
@@ -446,21 +444,18 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_Ck = take((size_t)Bi * kD * kRCols * 2);
   p.off_attS = take((size_t)Bi * T * R * 4);
   p.off_attB = take((size_t)Bi * T * R * 4);
-  const size_t tile_bytes = (size_t)Bi * kTileN * (kRCols * (4 + 2 + 4 + 2 + 2) + kD * (4 + 2) + 16);
-  size_t ct = ((size_t)4 << 30) / tile_bytes;
+  const size_t tile_bytes = (size_t)Bi * kTileN * (kRCols * 2 * 3 + kD * 2 + 4);
+  size_t ct = ((size_t)8 << 30) / tile_bytes;
   if (ct < 1) ct = 1;
   if (ct > (size_t)p.nt_max) ct = p.nt_max;
   p.ct = (int)ct;
   p.splits = std::min(Bi, 16);
   const size_t rows = (size_t)Bi * ct * kTileN;
-  p.off_S32 = take(rows * kRCols * 4);
   p.off_E16 = take(rows * kRCols * 2);
-  p.off_V32 = take(rows * kD * 4);
   p.off_dV16 = take(rows * kD * 2);
-  p.off_G32 = take(rows * kRCols * 4);
   p.off_DS16 = take(rows * kRCols * 2);
   p.off_A116 = take(rows * kRCols * 2);
-  p.off_stat = take(rows * 16);
+  p.off_dpp = take(rows * 4);
   p.off_dwp = take((size_t)p.splits * ct * kTileN * kD * 4);
   p.off_m = take((size_t)Bi * Bc * 4);
   p.total = o;
@@ -545,7 +540,6 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
   return check_launch("damsm_fwd_kernel");
 }
 
-#include "damsm_tc_bwd.inc"
 #include "damsm_tc_bwd2.inc"
 #include "damsm_tc_bwd2_host.inc"
 
@@ -594,14 +588,6 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
   if (workspace_bytes < pl.total) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
     return AGB_E_WORKSPACE;
-  }
-  static const bool staged = getenv("AGB_DAMSM_STAGED_BWD") != nullptr;   // round-1 staged backward, kept for A/B runs
-  if (staged) {
-    if (math == AGB_MATH_TC_BF16)
-      return tc::run_bwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale,
-                                        dimg, dwords, (char*)workspace, pl, st);
-    return tc::run_bwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, gscale, dimg,
-                               dwords, (char*)workspace, pl, st);
   }
   if (math == AGB_MATH_TC_BF16)
     return tc::run_bwd2<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd,

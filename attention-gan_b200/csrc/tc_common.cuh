@@ -43,8 +43,13 @@ struct TcGemmArgs {
   // independent batches; slice z writes its partial sum to C + z*c_z
   int split_kb, kb_total;
   int stages;                  // ring depth, set by tc_gemm()
+  int MT;                      // 128-row output tiles per CTA (1 or 2), sharing the B operand
+  int nsrc;                    // 1, or 2: a second (A2, B2) operand pair continues the same reduction
+  int64_t a2_zrow, b2_zrow;    // batch row offsets of the second pair
 };
 int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st);
+int tc_gemm2(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapA2,
+             const CUtensorMap& mapB2, int batch, cudaStream_t st);
 
 // ---- PTX wrappers (device) --------------------------------------------------------------------
 __device__ __forceinline__ bool elect_one() {

@@ -35,13 +35,15 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint3
 
 __global__ void __launch_bounds__(192)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
                const TcGemmArgs g) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full[kGemmStages], empty[kGemmStages], done;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * g.NT, m0 = blockIdx.y * 128, z = blockIdx.z;
+  const int MT = g.MT;                                  // 128-row tiles per CTA sharing the B operand
+  const int n0 = blockIdx.x * g.NT, m0 = blockIdx.y * 128 * MT, z = blockIdx.z;
   int kchunks = g.K >> 6;
   int kb_begin = 0, kb_count = g.KB;
   const int zb = g.split_kb ? 0 : z;                   // batch index used for operand offsets
@@ -56,9 +58,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     else kchunks = min(kchunks, (valid + 63) >> 6);
   }
   if (m0 >= m_valid) return;                           // whole CTA: nothing to do (before any barrier / alloc)
-  const int total = kb_count * kchunks;
+  const int per_src = kb_count * kchunks;
+  const int total = g.nsrc * per_src;
   const int stages = g.stages;
-  const int stage_bytes = kChunkBytes16 + g.NT * 128;
+  const int stage_bytes = MT * kChunkBytes16 + g.NT * 128;
+  const uint32_t tmem_cols = MT * g.NT <= 128 ? 128u : 256u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
@@ -68,7 +72,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     mbar_init(&done, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -76,28 +80,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 4) {
     if (elect_one()) {
-      const uint32_t bytes = (uint32_t)kChunkBytes16 + (uint32_t)g.NT * 128u;
+      const uint32_t bytes = (uint32_t)stage_bytes;
       for (int it = 0; it < total; ++it) {
         const int s = it % stages, use = it / stages;
-        const int kbl = it / kchunks, k0 = (it - kbl * kchunks) * 64;
+        const int src = it / per_src, r = it - src * per_src;
+        const int kbl = r / kchunks, k0 = (r - kbl * kchunks) * 64;
         const int kb = kb_begin + kbl;
+        const CUtensorMap* mA = src ? &mapA2 : &mapA;
+        const CUtensorMap* mB = src ? &mapB2 : &mapB;
         mbar_wait(&empty[s], (use & 1) ^ 1);
         mbar_expect_tx(&full[s], bytes);
         unsigned char* sa = smem + s * stage_bytes;
-        unsigned char* sb = sa + kChunkBytes16;
-        const int arow = (int)(zb * g.a_zrow + kb * g.a_kbrow), acol = (int)(zb * g.a_zcol + kb * g.a_kbcol);
-        const int brow = (int)(zb * g.b_zrow + kb * g.b_kbrow), bcol = (int)(zb * g.b_zcol + kb * g.b_kbcol);
-        if (!g.a_mn) {
-          tma_load_2d(sa, &mapA, &full[s], acol + k0, arow + m0);                 // [128 m][64 k]
-        } else {
-          tma_load_2d(sa, &mapA, &full[s], acol + m0, arow + k0);                 // [64 k][64 m] x 2
-          tma_load_2d(sa + 8192, &mapA, &full[s], acol + m0 + 64, arow + k0);
+        unsigned char* sb = sa + MT * kChunkBytes16;
+        const int64_t azr = src ? g.a2_zrow : g.a_zrow, bzr = src ? g.b2_zrow : g.b_zrow;
+        const int arow = (int)(zb * azr + kb * g.a_kbrow), acol = (int)(zb * g.a_zcol + kb * g.a_kbcol);
+        const int brow = (int)(zb * bzr + kb * g.b_kbrow), bcol = (int)(zb * g.b_zcol + kb * g.b_kbcol);
+        for (int mt = 0; mt < MT; ++mt) {
+          unsigned char* sam = sa + mt * kChunkBytes16;
+          const int mm = m0 + mt * 128;
+          if (!g.a_mn) {
+            tma_load_2d(sam, mA, &full[s], acol + k0, arow + mm);                 // [128 m][64 k]
+          } else {
+            tma_load_2d(sam, mA, &full[s], acol + mm, arow + k0);                 // [64 k][64 m] x 2
+            tma_load_2d(sam + 8192, mA, &full[s], acol + mm + 64, arow + k0);
+          }
         }
         if (!g.b_mn) {
-          tma_load_2d(sb, &mapB, &full[s], bcol + k0, brow + n0);                 // [NT n][64 k]
+          tma_load_2d(sb, mB, &full[s], bcol + k0, brow + n0);                    // [NT n][64 k]
         } else {
           for (int nb = 0; nb < g.NT / 64; ++nb)
-            tma_load_2d(sb + nb * 8192, &mapB, &full[s], bcol + n0 + nb * 64, brow + k0);
+            tma_load_2d(sb + nb * 8192, mB, &full[s], bcol + n0 + nb * 64, brow + k0);
         }
       }
     }
@@ -108,12 +120,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int s = it % stages, use = it / stages;
         mbar_wait(&full[s], use & 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * stage_bytes), sb = sa + kChunkBytes16;
+        const uint32_t sa = smem_u32(smem + s * stage_bytes), sb = sa + MT * kChunkBytes16;
         for (int kk = 0; kk < 4; ++kk) {
           // K-major: +32 B per 16 k inside the 128-B row; MN-major: +16 rows = 2048 B
-          const uint64_t da = g.a_mn ? make_desc_sw128_mn(sa + kk * 2048, 8192) : make_desc_sw128(sa) + 2 * kk;
           const uint64_t db = g.b_mn ? make_desc_sw128_mn(sb + kk * 2048, 8192) : make_desc_sw128(sb) + 2 * kk;
-          umma_f16(tmem, da, db, idesc, (it | kk) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t sam = sa + mt * kChunkBytes16;
+            const uint64_t da = g.a_mn ? make_desc_sw128_mn(sam + kk * 2048, 8192) : make_desc_sw128(sam) + 2 * kk;
+            umma_f16(tmem + mt * g.NT, da, db, idesc, (it | kk) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -125,53 +140,58 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
     }
     float* Cz = g.C + (int64_t)z * g.c_z;
-    if (g.c_n == 1) {
-      // n-contiguous output: transpose through shared memory (the operand ring is idle now) so that
-      // every warp writes whole rows -- coalesced for any row pitch / alignment
-      float* tile = reinterpret_cast<float*>(smem);          // [128][NT + 1]
-      const int pitch = g.NT + 1;
-      const int row = warp * 32 + lane;
-      for (int c0 = 0; c0 < g.NT; c0 += 32) {
-        float v[32];
-        if (total > 0) {
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-          tmem_ld_wait();
-        } else {
+    for (int mt = 0; mt < MT; ++mt) {
+      const int mbase = m0 + mt * 128;
+      if (mbase >= m_valid) break;
+      if (g.c_n == 1) {
+        // n-contiguous output: transpose through shared memory (the operand ring is idle now) so that
+        // every warp writes whole rows -- coalesced for any row pitch / alignment
+        float* tile = reinterpret_cast<float*>(smem);          // [128][NT + 1]
+        const int pitch = g.NT + 1;
+        const int row = warp * 32 + lane;
+        if (mt > 0) named_bar_sync(1, 128);                    // previous tile fully written out
+        for (int c0 = 0; c0 < g.NT; c0 += 32) {
+          float v[32];
+          if (total > 0) {
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * g.NT + c0, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;           // empty reduction: the sum is zero
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;           // empty reduction: the sum is zero
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tile[row * pitch + c0 + j] = v[j];
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tile[row * pitch + c0 + j] = v[j];
-      }
-      named_bar_sync(1, 128);
-      const int rows = min(128, m_valid - m0);
-      const int cols = min(g.NT, g.N - n0);
-      for (int r = warp; r < rows; r += 4) {
-        float* prow = Cz + (int64_t)(m0 + r) * g.c_m + n0;
-        for (int n = lane; n < cols; n += 32) {
-          const float x = g.alpha * tile[r * pitch + n];
-          prow[n] = g.accumulate ? (prow[n] + x) : x;
+        named_bar_sync(1, 128);
+        const int rows = min(128, m_valid - mbase);
+        const int cols = min(g.NT, g.N - n0);
+        for (int r = warp; r < rows; r += 4) {
+          float* prow = Cz + (int64_t)(mbase + r) * g.c_m + n0;
+          for (int n = lane; n < cols; n += 32) {
+            const float x = g.alpha * tile[r * pitch + n];
+            prow[n] = g.accumulate ? (prow[n] + x) : x;
+          }
         }
-      }
-    } else {
-      const int m = m0 + warp * 32 + lane;
-      for (int c0 = 0; c0 < g.NT; c0 += 32) {
-        float v[32];
-        if (total > 0) {
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-          tmem_ld_wait();
-        } else {
+      } else {
+        const int m = mbase + warp * 32 + lane;
+        for (int c0 = 0; c0 < g.NT; c0 += 32) {
+          float v[32];
+          if (total > 0) {
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * g.NT + c0, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        if (m < m_valid) {
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (m < m_valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < g.N) {
-              float* p = Cz + (int64_t)m * g.c_m + (int64_t)n * g.c_n;
-              const float x = g.alpha * v[j];
-              *p = g.accumulate ? (*p + x) : x;
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < g.N) {
+                float* p = Cz + (int64_t)m * g.c_m + (int64_t)n * g.c_n;
+                const float x = g.alpha * v[j];
+                *p = g.accumulate ? (*p + x) : x;
+              }
             }
           }
         }
@@ -180,29 +200,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
-int tc_gemm(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st) {
+int tc_gemm2(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapA2,
+             const CUtensorMap& mapB2, int batch, cudaStream_t st) {
   TcGemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
   if (g.K <= 0 || g.K % 64 || g.KB <= 0) return fail_arg("tc_gemm: K=%d must be a positive multiple of 64", g.K);
   if (g.NT != 64 && g.NT != 128) return fail_arg("tc_gemm: NT=%d", g.NT);
+  if (g.MT != 1 && g.MT != 2) g.MT = 1;
+  if (g.nsrc != 2) g.nsrc = 1;
   static bool attr_set = false;
   if (!attr_set) {
     AGB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     attr_set = true;
   }
-  dim3 grid(cdiv(g.N, g.NT), cdiv(g.M, 128), batch);
+  dim3 grid(cdiv(g.N, g.NT), cdiv(g.M, 128 * g.MT), batch);
   if (grid.y > 65535 || grid.z > 65535) return fail_unsupported("tc_gemm grid too large");
-  // short reductions get a short ring so that several CTAs share an SM and hide each other's prologue
-  const long long chunks = (long long)g.KB * (g.K / 64);
-  g.stages = (int)std::min<long long>(kGemmStages, std::max<long long>(2, chunks));
-  const int smem_bytes = std::max(g.stages * (kChunkBytes16 + g.NT * 128), 128 * (g.NT + 1) * 4) + 1024;
+  // ring depth: as deep as ~192 KB allows; short reductions get a short ring so that several CTAs
+  // share an SM and hide each other's prologue
+  const int stage_bytes = g.MT * kChunkBytes16 + g.NT * 128;
+  const long long chunks = (long long)g.nsrc * g.KB * (g.K / 64);
+  const int max_stages = std::min(kGemmStages, (kGemmSmem - 1024) / stage_bytes);
+  g.stages = (int)std::min<long long>(max_stages, std::max<long long>(2, chunks));
+  const int smem_bytes = std::max(g.stages * stage_bytes, 128 * (g.NT + 1) * 4) + 1024;
   const int slot = prof_begin(PROF_DAMSM_TC_BWD, st);
-  tc_gemm_kernel<<<grid, 192, smem_bytes, st>>>(mapA, mapB, g);
+  tc_gemm_kernel<<<grid, 192, smem_bytes, st>>>(mapA, mapB, mapA2, mapB2, g);
   prof_end(slot, st);
   return check_launch("tc_gemm_kernel");
+}
+
+int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st) {
+  TcGemmArgs h = g;
+  h.nsrc = 1;
+  return tc_gemm2(h, mapA, mapB, mapA, mapB, batch, st);
 }
 
 }  // namespace tc

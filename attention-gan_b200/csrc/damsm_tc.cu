@@ -81,9 +81,9 @@ __global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, i
     if (threadIdx.x == 0) {
       for (int k = 0; k < n; ++k) {
         const int i = base + k, L = lens_s[k];
-        // the epilogues read a caption's TMEM columns in windows of 8: keep the whole window inside the
+        // the epilogues read a caption's TMEM columns in windows of 4: keep the whole window inside the
         // tile (the last accumulator buffer ends at TMEM column 512)
-        if (row + ((L + 7) & ~7) > kTileN || i - first == 128) {
+        if (row + ((L + 3) & ~3) > kTileN || i - first == 128) {
           tile_first[tile] = first;
           tile_ncap[tile] = i - first;
           ++tile;
@@ -148,43 +148,65 @@ __global__ void pack_img_kernel_tc(const float* __restrict__ img, T16* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue 1 for one caption: NL = caption length rounded up to a multiple of 8
+// epilogue 1 for one caption and one region (thread): NL = caption length rounded up to 4.
+// Branch-free: slots t >= L are set to -inf (their exponentials are 0) and only their stores are
+// predicated; slots below NL-4 are always live, so they carry no predicate at all.
 // ---------------------------------------------------------------------------------------------
+template <typename T16> __device__ __forceinline__ uint16_t bits16(float v) {
+  const T16 h = cvt16<T16>(v);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+
 template <typename T16, int NL>
-__device__ __forceinline__ void caption_softmax(uint32_t taddr, int L, int off, int r, int R, unsigned char* sE,
+__device__ __forceinline__ void caption_softmax(uint32_t taddr, int L, int off, int r, int R, uint32_t sE32,
                                                 float scale_log2, float g1_log2) {
   float s[NL];
-  if constexpr (NL == 8) tmem_ld8(taddr, s);
-  else if constexpr (NL == 16) tmem_ld16(taddr, s);
-  else if constexpr (NL == 24) { tmem_ld16(taddr, s); tmem_ld8(taddr + 16, s + 16); }
-  else tmem_ld32(taddr, s);
+  tmem_ld_n<NL>(taddr, s);
   tmem_ld_wait();
   if (r >= kRCols) return;
-  unsigned char* col = sE + (size_t)(r >> 6) * kChunk;
-  const int rc = r & 63;
+  // element (row n, col r) of the K-major 128B-swizzled e tile: chunk (r>>6), 16-byte unit ((r&63)>>3) ^ (n&7)
+  const uint32_t colbase = sE32 + (uint32_t)(r >> 6) * kChunk + ((r & 7) << 1) + (uint32_t)off * 128;
+  const uint32_t x = ((r & 63) >> 3) << 4;
   if (r >= R) {  // padding regions contribute nothing to V
 #pragma unroll
     for (int t = 0; t < NL; ++t)
-      if (t < L) *reinterpret_cast<T16*>(col + sw128_off(off + t, rc)) = cvt16<T16>(0.f);
+      if (t < NL - 4 || t < L) st_shared_u16(colbase + t * 128 + ((((off + t) << 4) & 0x70) ^ x), 0);
     return;
   }
-  float mx = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < NL; ++t)
-    if (t < L) mx = fmaxf(mx, s[t]);
-  float sum = 0.f;
-  const float mxs = mx * scale_log2;
+  for (int t = NL - 4; t < NL; ++t)
+    if (t >= L) s[t] = -INFINITY;
+  float m4[4];
 #pragma unroll
-  for (int t = 0; t < NL; ++t)
-    if (t < L) {
-      s[t] = exp2f(fmaf(s[t], scale_log2, -mxs));  // exp((s - max)/sqrt(D))
-      sum += s[t];
-    }
-  const float k = g1_log2 / sum;
+  for (int k = 0; k < 4; ++k) m4[k] = s[k];
 #pragma unroll
-  for (int t = 0; t < NL; ++t)
-    if (t < L) *reinterpret_cast<T16*>(col + sw128_off(off + t, rc)) = cvt16<T16>(exp2f(s[t] * k));  // exp(gamma1 alpha)
+  for (int t = 4; t < NL; ++t) m4[t & 3] = fmaxf(m4[t & 3], s[t]);
+  const float mxs = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < NL; ++t) {
+    s[t] = exp2f(fmaf(s[t], scale_log2, -mxs));  // exp((s - max)/sqrt(D))
+    s4[t & 3] += s[t];
+  }
+  const float k = g1_log2 / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+#pragma unroll
+  for (int t = 0; t < NL; ++t) {
+    const uint16_t e = bits16<T16>(exp2f(s[t] * k));  // exp(gamma1 alpha)
+    if (t < NL - 4 || t < L) st_shared_u16(colbase + t * 128 + ((((off + t) << 4) & 0x70) ^ x), e);
+  }
 }
+
+#define AGB_CAPTION_SWITCH(L, CALL)                       \
+  switch (((L) + 3) >> 2) {                               \
+    case 1: { constexpr int NL = 4; CALL; } break;        \
+    case 2: { constexpr int NL = 8; CALL; } break;        \
+    case 3: { constexpr int NL = 12; CALL; } break;       \
+    case 4: { constexpr int NL = 16; CALL; } break;       \
+    case 5: { constexpr int NL = 20; CALL; } break;       \
+    case 6: { constexpr int NL = 24; CALL; } break;       \
+    case 7: { constexpr int NL = 28; CALL; } break;       \
+    default: { constexpr int NL = 32; CALL; } break;      \
+  }
 
 struct FwdParams {
   const int32_t* tile_first;
@@ -197,222 +219,6 @@ struct FwdParams {
   int Bi, Bc, T, R;
   float scale_log2, g1_log2, gamma2;
 };
-
-template <typename T16>
-__global__ void __launch_bounds__(kThreads, 1)
-damsm_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapCt,
-                 const __grid_constant__ CUtensorMap mapCk, const FwdParams p) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-  unsigned char* sW = smem + kSmemW;
-  unsigned char* sE = smem + kSmemE;
-  unsigned char* sRing = smem + kSmemRing;
-  __shared__ uint64_t w_full, w_empty, slot_full[2], slot_empty[2], s_full[3], s_empty[2], e_ready, v_full, v_empty;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ int cap_off_s[128], cap_len_s[128];
-  __shared__ float2 part_s[3][128];
-  __shared__ float cos_s[128];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nct = p.ntiles[0];
-  const int total = p.Bi * nct;
-  const int NMT = (p.R + 127) >> 7;
-  const int RKC = (p.R + 63) >> 6;
-  const int last_ks = ((p.R - (RKC - 1) * 64) + 15) >> 4;
-  constexpr int fmt = sizeof(T16) == 2 && std::is_same<T16, __nv_bfloat16>::value ? 1 : 0;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&w_full, 1);
-    mbar_init(&w_empty, 12);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&slot_full[i], 1);
-      mbar_init(&slot_empty[i], 1);
-      mbar_init(&s_empty[i], 4);
-    }
-    // one "scores ready" barrier per M-tile (one phase per work item): a parity wait is only safe
-    // when the waiter is at most one phase ahead, which a per-buffer barrier would not guarantee
-    for (int i = 0; i < 3; ++i) mbar_init(&s_full[i], 1);
-    mbar_init(&e_ready, 12);
-    mbar_init(&v_full, 1);
-    mbar_init(&v_empty, 12);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(&tmem_base_s, 512);
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapW);
-    prefetch_tmap(&mapCt);
-    prefetch_tmap(&mapCk);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      uint32_t slot_it = 0;
-      int tile_it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tile_it) {
-        const int b = tile / nct, c = tile - b * nct;
-        mbar_wait(&w_empty, (tile_it & 1) ^ 1);
-        mbar_expect_tx(&w_full, 4 * kChunk);
-        for (int kc = 0; kc < 4; ++kc) tma_load_2d(sW + kc * kChunk, &mapW, &w_full, kc * 64, c * kTileN);
-        for (int j = 0; j < NMT; ++j)
-          for (int h = 0; h < 2; ++h, ++slot_it) {
-            const int s = slot_it & 1;
-            mbar_wait(&slot_empty[s], ((slot_it >> 1) & 1) ^ 1);
-            mbar_expect_tx(&slot_full[s], kSlot);
-            for (int q = 0; q < 2; ++q)
-              tma_load_2d(sRing + s * kSlot + q * kChunk, &mapCt, &slot_full[s], (2 * h + q) * 64, b * kRRows + j * 128);
-          }
-        for (int rc = 0; rc < RKC; ++rc, ++slot_it) {
-          const int s = slot_it & 1;
-          mbar_wait(&slot_empty[s], ((slot_it >> 1) & 1) ^ 1);
-          mbar_expect_tx(&slot_full[s], kSlot);
-          tma_load_2d(sRing + s * kSlot, &mapCk, &slot_full[s], rc * 64, b * kD);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc1 = make_idesc(128, 128, fmt);
-      constexpr uint32_t idesc2 = make_idesc(128, 256, fmt);
-      uint32_t slot_it = 0, sbuf_it = 0;
-      int tile_it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tile_it) {
-        mbar_wait(&w_full, tile_it & 1);
-        tc_fence_after();
-        for (int j = 0; j < NMT; ++j, ++sbuf_it) {
-          const int buf = sbuf_it & 1;
-          mbar_wait(&s_empty[buf], ((sbuf_it >> 1) & 1) ^ 1);
-          tc_fence_after();
-          for (int h = 0; h < 2; ++h, ++slot_it) {
-            const int s = slot_it & 1;
-            mbar_wait(&slot_full[s], (slot_it >> 1) & 1);
-            tc_fence_after();
-            for (int q = 0; q < 2; ++q) {
-              const uint64_t da = make_desc_sw128(smem_u32(sRing + s * kSlot + q * kChunk));
-              const uint64_t db = make_desc_sw128(smem_u32(sW + (2 * h + q) * kChunk));
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16(tmem + buf * 128, da + 2 * kk, db + 2 * kk, idesc1, (h | q | kk) ? 1u : 0u);
-            }
-            umma_commit(&slot_empty[s]);
-          }
-          umma_commit(&s_full[j]);
-        }
-        mbar_wait(&e_ready, tile_it & 1);
-        mbar_wait(&v_empty, (tile_it & 1) ^ 1);
-        tc_fence_after();
-        for (int rc = 0; rc < RKC; ++rc, ++slot_it) {
-          const int s = slot_it & 1;
-          mbar_wait(&slot_full[s], (slot_it >> 1) & 1);
-          tc_fence_after();
-          const uint64_t da = make_desc_sw128(smem_u32(sE + rc * kChunk));
-          const uint64_t db = make_desc_sw128(smem_u32(sRing + s * kSlot));
-          const int ks = (rc == RKC - 1) ? last_ks : 4;
-          for (int kk = 0; kk < ks; ++kk) umma_f16(tmem + 256, da + 2 * kk, db + 2 * kk, idesc2, (rc | kk) ? 1u : 0u);
-          umma_commit(&slot_empty[s]);
-        }
-        umma_commit(&v_full);
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue warpgroups =====================
-    const int wg = (warp - 4) >> 2;
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int lrow = q * 32 + lane;               // TMEM lane: region within the M-tile / word row
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int etid = threadIdx.x - 128;
-    int tile_it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tile_it) {
-      const int b = tile / nct, c = tile - b * nct;
-      const int ncap = p.tile_ncap[c], first = p.tile_first[c];
-      if (etid < ncap) {
-        cap_off_s[etid] = p.cap_row[first + etid] - c * kTileN;
-        cap_len_s[etid] = min(max(p.cap_lens[first + etid], 0), p.T);
-      }
-      named_bar_sync(1, 384);
-      // ---- epilogue 1: both softmaxes of M-tile wg -------------------------------------------
-      if (wg < NMT) {
-        const uint32_t sbuf_it = (uint32_t)tile_it * NMT + wg;
-        const int buf = sbuf_it & 1;
-        mbar_wait(&s_full[wg], tile_it & 1);
-        tc_fence_after();
-        const int r = wg * 128 + lrow;
-        for (int cc = 0; cc < ncap; ++cc) {
-          const int off = cap_off_s[cc], L = cap_len_s[cc];
-          if (L == 0) continue;
-          const uint32_t taddr = tmem + lane_addr + buf * 128 + off;
-          switch ((L + 7) >> 3) {
-            case 1: caption_softmax<T16, 8>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
-            case 2: caption_softmax<T16, 16>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
-            case 3: caption_softmax<T16, 24>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
-            default: caption_softmax<T16, 32>(taddr, L, off, r, p.R, sE, p.scale_log2, p.g1_log2); break;
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[buf]);
-      }
-      fence_proxy_async();   // e (generic-proxy stores) -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&e_ready);
-      // ---- epilogue 2: cosine per word, log-sum-exp per caption --------------------------------
-      mbar_wait(&v_full, tile_it & 1);
-      mbar_wait(&w_full, tile_it & 1);   // the TMA-written word tile is read below through the generic proxy
-      tc_fence_after();
-      float accn = 0.f, accq = 0.f;
-      for (int ch = wg; ch < 8; ch += 3) {
-        float v[32];
-        tmem_ld32(tmem + lane_addr + 256 + ch * 32, v);
-        tmem_ld_wait();
-        const unsigned char* wrow = sW + (size_t)(ch >> 1) * kChunk + lrow * 128;
-        const int u0 = (ch & 1) * 4;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint4 wv = *reinterpret_cast<const uint4*>(wrow + ((((u0 + u) ^ (lrow & 7)) & 7) << 4));
-          const uint32_t wr[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 w2 = unpack2<T16>(wr[k]);
-            accn = fmaf(w2.x, v[u * 8 + 2 * k], accn);
-            accn = fmaf(w2.y, v[u * 8 + 2 * k + 1], accn);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) accq = fmaf(v[k], v[k], accq);
-      }
-      part_s[wg][lrow] = make_float2(accn, accq);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&v_empty);   // V drained from TMEM
-        mbar_arrive(&w_empty);   // word tile no longer read
-      }
-      named_bar_sync(1, 384);
-      if (wg == 0) {
-        const float2 a = part_s[0][lrow], b2 = part_s[1][lrow], c2 = part_s[2][lrow];
-        const float nn = a.x + b2.x + c2.x;
-        const float qq = sqrtf(a.y + b2.y + c2.y);
-        const float den = fmaxf(p.pn[(size_t)c * kTileN + lrow] * qq, 1e-30f);
-        cos_s[lrow] = nn / den;
-        named_bar_sync(2, 128);
-        if (lrow < ncap) {
-          const int off = cap_off_s[lrow], L = cap_len_s[lrow];
-          float sum = 0.f;
-          for (int t = 0; t < L; ++t) sum += __expf(p.gamma2 * cos_s[off + t]);
-          p.m_out[(size_t)b * p.Bc + first + lrow] = logf(sum);                      // words_loss.py:77-79
-        }
-      }
-      named_bar_sync(1, 384);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
-}
 
 #include "damsm_tc_fwd2.inc"
 
@@ -430,7 +236,7 @@ struct TcPlan {
 
 static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   TcPlan p;
-  const int per_tile = 128 / ((T + 7) & ~7);  // captions that always fit in one tile (8-column windows)
+  const int per_tile = 128 / ((T + 3) & ~3);  // captions that always fit in one tile (4-column windows)
   p.nt_max = (Bc + per_tile - 1) / per_tile;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 1024); return at; };

@@ -118,6 +118,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt) {
 }
 
 // TMEM -> registers: this warp's 32 lanes x NC consecutive 32-bit columns (thread i <- lane base+i)
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -142,6 +148,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+// NL (multiple of 4, <= 32) consecutive columns
+template <int NL>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
+  if constexpr (NL >= 32) tmem_ld32(taddr, v);
+  else if constexpr (NL >= 16) { tmem_ld16(taddr, v); if constexpr (NL > 16) tmem_ld_n<NL - 16>(taddr + 16, v + 16); }
+  else if constexpr (NL >= 8) { tmem_ld8(taddr, v); if constexpr (NL > 8) tmem_ld_n<NL - 8>(taddr + 8, v + 8); }
+  else tmem_ld4(taddr, v);
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -60,6 +60,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (m0 >= m_valid) return;                           // whole CTA: nothing to do (before any barrier / alloc)
   const int per_src = kb_count * kchunks;
   const int total = g.nsrc * per_src;
+  if (total == 0 && g.accumulate) return;              // empty reduction added to C: nothing to do
   const int stages = g.stages;
   const int stage_bytes = MT * kChunkBytes16 + g.NT * 128;
   const uint32_t tmem_cols = MT * g.NT <= 128 ? 128u : 256u;

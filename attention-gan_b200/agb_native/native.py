@@ -43,7 +43,7 @@ SIGNATURES = {
                               c_void_p]),
     "agb_damsm_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int,
                               c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "agb_sent_cos_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "agb_sent_cos_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "agb_sent_cos_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

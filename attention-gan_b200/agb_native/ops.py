@@ -97,9 +97,10 @@ def damsm_supported(T: int, D: int, R: int, math: int) -> bool:
 def damsm_fwd(img: torch.Tensor, words: torch.Tensor, cap_lens: torch.Tensor, gamma1: float,
               gamma2: float, eps: float = 1e-8, row_offset: int = 0, want_att: bool = True,
               math: int = N.AGB_MATH_FP32, cnn: Optional[torch.Tensor] = None,
-              rnn: Optional[torch.Tensor] = None):
+              rnn: Optional[torch.Tensor] = None, keep_ws: bool = False):
     """img [Bi,D,R] fp32 contiguous, words [Bc,D,T] fp32 (any strides), cap_lens [Bc] int32.
-    Returns (m [Bi,Bc], att [Bi,T,R] or None, scos [Bi,Bc] or None)."""
+    Returns (m [Bi,Bc], att [Bi,T,R] or None, scos [Bi,Bc] or None); with keep_ws also the workspace
+    tensor, whose packed operands damsm_bwd(ws=...) can reuse."""
     require_cuda(img, words, cap_lens, cnn, rnn)
     Bi, D, R = img.shape
     Bc, _, T = words.shape
@@ -115,11 +116,14 @@ def damsm_fwd(img: torch.Tensor, words: torch.Tensor, cap_lens: torch.Tensor, ga
                                _p(cap_lens), Bi, Bc, T, D, R, gamma1, gamma2, eps, row_offset, _p(m),
                                _p(att), _p(cnn), _p(rnn), _p(scos), _p(ws), ws.numel(), math, _stream(img))
     N.check(rc, "agb_damsm_fwd")
+    if keep_ws:
+        return m, att, scos, ws
     return m, att, scos
 
 
 def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords: bool,
-              math: int = N.AGB_MATH_FP32, m_fwd: Optional[torch.Tensor] = None):
+              math: int = N.AGB_MATH_FP32, m_fwd: Optional[torch.Tensor] = None,
+              ws: Optional[torch.Tensor] = None):
     """dm [Bi,Bc] = dLoss/dm, gscale: device scalar or None.
     Returns (dimg [Bi,D,R], dwords [Bc,T,D] word-major or None)."""
     require_cuda(img, words, cap_lens, dm, gscale)
@@ -128,10 +132,12 @@ def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords
     dev = img.device
     dimg = torch.empty_like(img)
     dwords = torch.empty((Bc, T, D), dtype=torch.float32, device=dev) if need_dwords else None
-    ws = _ws(N.lib().agb_damsm_workspace_bytes(Bi, Bc, T, D, R, math), dev)
+    from_fwd = int(ws is not None)
+    if ws is None:
+        ws = _ws(N.lib().agb_damsm_workspace_bytes(Bi, Bc, T, D, R, math), dev)
     rc = N.lib().agb_damsm_bwd(_p(img), _p(words), words.stride(0), words.stride(1), words.stride(2),
                                _p(cap_lens), Bi, Bc, T, D, R, gamma1, gamma2, eps, _p(dm), _p(m_fwd), _p(gscale),
-                               _p(dimg), _p(dwords), _p(ws), ws.numel(), math, _stream(img))
+                               _p(dimg), _p(dwords), _p(ws), ws.numel(), from_fwd, math, _stream(img))
     N.check(rc, "agb_damsm_bwd")
     return dimg, dwords
 

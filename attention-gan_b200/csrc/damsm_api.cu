@@ -25,7 +25,7 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
 int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1,
                  float gamma2, float eps, const float* dm, const float* m_fwd, const float* gscale, float* dimg,
-                 float* dwords, void* workspace, size_t workspace_bytes, int math, cudaStream_t st);
+                 float* dwords, void* workspace, size_t workspace_bytes, int ws_from_fwd, int math, cudaStream_t st);
 #endif
 }  // namespace agb
 
@@ -87,7 +87,7 @@ extern "C" int agb_damsm_bwd(const float* img, const float* words, int64_t ws_b,
                              int64_t ws_t, const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R,
                              float gamma1, float gamma2, float eps, const float* dm, const float* m_fwd,
                              const float* gscale, float* dimg, float* dwords, void* workspace,
-                             size_t workspace_bytes, int math, void* stream) {
+                             size_t workspace_bytes, int ws_from_fwd, int math, void* stream) {
   if (!img || !words || !cap_lens || !dm || !dimg || !workspace) return fail_arg("null pointer");
   if (!agb_damsm_supported(T, D, R, math)) return fail_unsupported("T=%d D=%d R=%d math=%d is outside the compiled range", T, D, R, math);
   cudaStream_t st = (cudaStream_t)stream;
@@ -96,7 +96,7 @@ extern "C" int agb_damsm_bwd(const float* img, const float* words, int64_t ws_b,
                           gscale, dimg, dwords, workspace, workspace_bytes, st);
 #ifdef AGB_WITH_TC
   return damsm_tc_bwd(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, D, R, gamma1, gamma2, eps, dm, m_fwd, gscale,
-                      dimg, dwords, workspace, workspace_bytes, math, st);
+                      dimg, dwords, workspace, workspace_bytes, ws_from_fwd, math, st);
 #else
   return fail_unsupported("library built without the tcgen05 kernels");
 #endif

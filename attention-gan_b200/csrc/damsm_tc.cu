@@ -14,8 +14,8 @@
 //
 // Operands reach the tensor core by TMA (128B swizzle, K-major); accumulators live in TMEM:
 // columns [0,256) = two S buffers (MMA of M-tile j+1 overlaps epilogue 1 of M-tile j),
-// columns [256,512) = V.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
-// 4..15 = three epilogue warpgroups (one per M-tile).
+// columns [256,512) = V.  Warp roles: 0..11 = three epilogue warpgroups, 12 = TMA producer and
+// TMEM allocator, 13 = MMA issuer (448 threads: 144 registers per thread for the epilogues).
 //
 // HBM layout of the pre-packed operands (written by the pack kernels below, 16-bit):
 //   Wh [tiles*128, 256]   packed caption words, K-major rows; unused rows are zero
@@ -47,7 +47,7 @@ constexpr int kRRows = 384;               // region rows per image in Ct (3 M-ti
 constexpr int kRCols = 320;               // region columns per image in Ck / e (5 chunks of 64)
 constexpr int kChunk = 128 * 128;         // one [128 x 64] 16-bit K-major tile: 16 KB
 constexpr int kSlot = 2 * kChunk;         // ring slot: 32 KB
-constexpr int kThreads = 512;
+constexpr int kThreads = 448;             // warps 0-11 epilogue, 12 TMA producer (+ TMEM alloc), 13 MMA issuer
 constexpr int kSmemW = 0;                 // [4][128 x 64]  resident word tile       64 KB
 constexpr int kSmemE = 4 * kChunk;        // [5][128 x 64]  e = exp(gamma1 alpha)    80 KB
 constexpr int kSmemRing = 9 * kChunk;     // 2 slots                                  64 KB
@@ -287,7 +287,7 @@ struct Packed {
 template <typename T16>
 static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                     const int32_t* cap_lens, int Bi, int Bc, int T, int R, char* ws, const TcPlan& pl, Packed* out,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool already_packed = false) {
   T16* Wh = (T16*)(ws + pl.off_Wh);
   float* pn = (float*)(ws + pl.off_pn);
   int32_t* cap_row = (int32_t*)(ws + pl.off_caprow);
@@ -296,14 +296,16 @@ static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t 
   int32_t* ntiles = (int32_t*)(ws + pl.off_ntiles);
   T16* Ct = (T16*)(ws + pl.off_Ct);
   T16* Ck = (T16*)(ws + pl.off_Ck);
-  AGB_CUDA(cudaMemsetAsync(Wh, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
-  AGB_CUDA(cudaMemsetAsync(pn, 0, (size_t)pl.nt_max * kTileN * 4, st));
-  tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, cap_row, tfirst, tncap, ntiles);
-  if (int rc = check_launch("tile_pack_kernel")) return rc;
-  pack_words_kernel_tc<T16><<<dim3(Bc, T), 128, 0, st>>>(words, ws_b, ws_d, ws_t, cap_lens, cap_row, Wh, pn, T);
-  if (int rc = check_launch("pack_words_kernel_tc")) return rc;
-  pack_img_kernel_tc<T16><<<dim3(kRRows / 32, kD / 32, Bi), dim3(32, 8), 0, st>>>(img, Ck, Ct, R);
-  if (int rc = check_launch("pack_img_kernel_tc")) return rc;
+  if (!already_packed) {
+    AGB_CUDA(cudaMemsetAsync(Wh, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
+    AGB_CUDA(cudaMemsetAsync(pn, 0, (size_t)pl.nt_max * kTileN * 4, st));
+    tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, cap_row, tfirst, tncap, ntiles);
+    if (int rc = check_launch("tile_pack_kernel")) return rc;
+    pack_words_kernel_tc<T16><<<dim3(Bc, T), 128, 0, st>>>(words, ws_b, ws_d, ws_t, cap_lens, cap_row, Wh, pn, T);
+    if (int rc = check_launch("pack_words_kernel_tc")) return rc;
+    pack_img_kernel_tc<T16><<<dim3(kRRows / 32, kD / 32, Bi), dim3(32, 8), 0, st>>>(img, Ck, Ct, R);
+    if (int rc = check_launch("pack_img_kernel_tc")) return rc;
+  }
   out->Wh = Wh; out->pn = pn; out->cap_row = cap_row; out->tfirst = tfirst; out->tncap = tncap; out->ntiles = ntiles;
   out->Ct = Ct; out->Ck = Ck;
   return 0;
@@ -387,7 +389,7 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
 int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
                  float eps, const float* dm, const float* m_fwd, const float* gscale, float* dimg, float* dwords,
-                 void* workspace, size_t workspace_bytes, int math, cudaStream_t st) {
+                 void* workspace, size_t workspace_bytes, int ws_from_fwd, int math, cudaStream_t st) {
   if (Bi <= 0 || Bc <= 0) return fail_arg("non-positive batch");
   if (Bi > 65535) return fail_unsupported("Bi=%d > 65535", Bi);
   const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R);
@@ -397,9 +399,9 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
   }
   if (math == AGB_MATH_TC_BF16)
     return tc::run_bwd2<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd,
-                                       gscale, dimg, dwords, (char*)workspace, pl, st);
+                                       gscale, dimg, dwords, (char*)workspace, pl, ws_from_fwd, st);
   return tc::run_bwd2<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd, gscale,
-                              dimg, dwords, (char*)workspace, pl, st);
+                              dimg, dwords, (char*)workspace, pl, ws_from_fwd, st);
 }
 
 }  // namespace agb

@@ -115,8 +115,9 @@ class _WordsLossFn(torch.autograd.Function):
             rnn32 = rnn.detach().float().reshape(rnn.shape[-2], -1).contiguous()
             if ex.W > 1:
                 rnn32 = _gather_cat(rnn32, cfg.group)
-        m, att, scos = o.damsm_fwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, ex.row0, cfg.want_att,
-                                   cfg.math, cnn32 if fuse_sent else None, rnn32 if fuse_sent else None)
+        m, att, scos, ws = o.damsm_fwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, ex.row0, cfg.want_att,
+                                       cfg.math, cnn32 if fuse_sent else None, rnn32 if fuse_sent else None, True)
+        ctx.ws = ws if cfg.math != native.AGB_MATH_FP32 else None    # packed 16-bit operands, reused by backward
         m_all = _gather_cat(m, cfg.group) if ex.W > 1 else m
         loss, dm = o.contrastive(m_all, ex.cls, ex.labels, cfg.gamma3, cfg.lam, ex.row0, Bl)
         ctx.save_for_backward(img3, w32, dm, m)
@@ -141,7 +142,8 @@ class _WordsLossFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[1]
         gscale = dloss.detach().float().reshape(1).contiguous()
         dimg, dwords = cfg.ops.damsm_bwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, dm, gscale, need_w,
-                                         cfg.math, m)
+                                         cfg.math, m, ctx.ws)
+        ctx.ws = None
         if dwords is not None:
             if ex.W > 1:
                 dwords = _reduce_scatter_sum(dwords, cfg.group)

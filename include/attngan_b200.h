@@ -140,6 +140,8 @@ int agb_damsm_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws
  *   dm      [Bi,Bc]  fp32: dLoss/dm (already includes gamma3 and lambda, see agb_contrastive)
  *   m_fwd   [Bi,Bc]  fp32: m_out of the matching agb_damsm_fwd call, or NULL (then the tensor-core
  *                    path recomputes it; the fp32 path does not need it)
+ *   ws_from_fwd      != 0: `workspace` is the untouched buffer the matching agb_damsm_fwd call (same
+ *                    inputs, same math) used; the tensor-core path then reuses its packed operands
  *   gscale  device scalar (upstream d/dloss) or NULL for 1
  *   dimg    [Bi,D,R] fp32 out (overwritten)
  *   dwords  [Bc,T,D] fp32 contiguous out (note: word-major, the RNN's physical layout), or NULL
@@ -148,8 +150,8 @@ int agb_damsm_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws
 int agb_damsm_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                   const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1,
                   float gamma2, float eps, const float* dm, const float* m_fwd, const float* gscale,
-                  float* dimg, float* dwords, void* workspace, size_t workspace_bytes, int math,
-                  void* stream);
+                  float* dimg, float* dwords, void* workspace, size_t workspace_bytes,
+                  int ws_from_fwd, int math, void* stream);
 
 /* returns 1 when (T, D, R, math) is inside the compiled range of the requested path */
 int agb_damsm_supported(int T, int D, int R, int math);

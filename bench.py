@@ -226,10 +226,11 @@ def run_native(args):
         mean_len = float(lens_h.float().mean())
         lens_h = lens_h[sl].contiguous().pin_memory()
         cls_np = torch.randint(0, 500, (Bg,), generator=g, dtype=torch.int64)[sl].numpy()
+        cls_h = torch.from_numpy(cls_np).to(torch.int32).pin_memory()
         labels = torch.arange(Bl, device=dev)
         loss_mod = pkg.DAMSMLoss(dev, math=args.math, process_group=group, att_maps="packed")
         out_h = torch.empty(2, dtype=torch.float32).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in (img_h, wrd_h, cnn_h, rnn_h, lens_h)) + cls_np.nbytes
+        h2d = sum(t.numel() * t.element_size() for t in (img_h, wrd_h, cnn_h, rnn_h, lens_h, cls_h))
         d2h = 8
 
         def make_dev():
@@ -253,7 +254,8 @@ def run_native(args):
                   rnn_h.to(dev, non_blocking=True).requires_grad_(True),
                   lens_h.to(dev, non_blocking=True)]
             img, wrd, cnn, rnn, lens = ts
-            wl, sls, _ = loss_mod.get_losses(img, cnn, wrd.transpose(1, 2), rnn, labels, lens, cls_np)
+            wl, sls, _ = loss_mod.get_losses(img, cnn, wrd.transpose(1, 2), rnn, labels, lens,
+                                             cls_h.to(dev, non_blocking=True))
             (wl + sls).backward()
             out_h[0:1].copy_(wl.detach().reshape(1), non_blocking=True)
             out_h[1:2].copy_(sls.detach().reshape(1), non_blocking=True)
@@ -322,50 +324,74 @@ def run_native(args):
         tags = [4, 5]
         dtype = "f32"          # arithmetic is fp32 in registers; I/O dtype is in config
 
-    # ---- device-resident timing ---------------------------------------------------------------
+    def capture(step):
+        """CUDA-graph capture of one whole step (single process only); None if capture is not possible"""
+        if world > 1 or args.no_graph:
+            return None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            torch.cuda.synchronize()
+            return g
+        except Exception as e:                     # pragma: no cover
+            sys.stderr.write(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); timing eagerly\n")
+            torch.cuda.synchronize()
+            return None
+
+    def timed(run):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for a, b in ev:
+            flush.zero_()                         # L2 flush between timed iterations (outside the events)
+            a.record()
+            run()
+            b.record()
+        barrier()
+        sec = sum(a.elapsed_time(b) for a, b in ev) / 1e3 / args.steps
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- per-kernel durations: eager profiling pass (CUDA events recorded by the library) -------
     ts = make_dev()
     for _ in range(args.warmup):
         step_dev(ts)
     barrier()
+    prof_steps = min(args.steps, 5)
+    lib.agb_prof_enable(1)
+    n0 = lib.agb_launch_count()
+    for _ in range(prof_steps):
+        flush.zero_()
+        step_dev(ts)
+    barrier()
+    launches_per_step = (lib.agb_launch_count() - n0) // prof_steps
+    prof = {t: prof_read(lib, t) for t in tags}
+    lib.agb_prof_enable(0)
+
+    # ---- device-resident timing (the step replayed from a CUDA graph when possible) -------------
+    graph = capture(lambda: step_dev(ts))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    lib.agb_prof_enable(1)
-    n0 = lib.agb_launch_count()
-    barrier()
-    for a, b in ev:
-        flush.zero_()                         # L2 flush between timed iterations (outside the events)
-        a.record()
-        step_dev(ts)
-        b.record()
-    barrier()
-    launches = lib.agb_launch_count() - n0
+    sec = timed(graph.replay if graph is not None else (lambda: step_dev(ts)))
     clocks = sampler.stop() if rank == 0 else None
-    prof = {t: prof_read(lib, t) for t in tags}
-    lib.agb_prof_enable(0)
-    sec = sum(a.elapsed_time(b) for a, b in ev) / 1e3 / args.steps
-    tsec = torch.tensor([sec], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
-    sec = float(tsec.item())
+    launches = launches_per_step * args.steps
 
     # ---- end to end through the public API with host buffers -----------------------------------
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in ev2:
-        flush.zero_()
-        a.record()
-        step_e2e()
-        b.record()
-    barrier()
-    sec2 = sum(a.elapsed_time(b) for a, b in ev2) / 1e3 / args.steps
-    tsec2 = torch.tensor([sec2], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tsec2, op=dist.ReduceOp.MAX)
-    sec2 = float(tsec2.item())
+    graph2 = capture(step_e2e)
+    sec2 = timed(graph2.replay if graph2 is not None else step_e2e)
 
     if rank != 0:
         if world > 1:
@@ -376,7 +402,7 @@ def run_native(args):
     if damsm:
         ms_tot = sum(prof[t][0] for t in tags)
         n_l = sum(prof[t][1] for t in tags)
-        flops = flop_per_unit * units * args.steps            # algorithmic flops the launches covered
+        flops = flop_per_unit * units * prof_steps            # algorithmic flops the profiled launches covered
         ach = flops / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
         peak = peaks["tf_burst"]
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -386,13 +412,13 @@ def run_native(args):
                 "algorithmic": "12*R*mean(cap_len)*D flop per (image,caption) pair, fwd+bwd"}
     else:
         (ms_f, n_f), (ms_b, n_b) = prof[4], prof[5]
-        gb = (bytes_fwd + bytes_bwd) * units * args.steps / 1e9
+        gb = (bytes_fwd + bytes_bwd) * units * prof_steps / 1e9
         ach = gb / ((ms_f + ms_b) * 1e-3) if ms_f + ms_b > 0 else 0.0
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                 "traffic": None, "kernel": "word_attn_fwd_kernel + word_attn_bwd_kernel",
                 "launches": int(n_f + n_b), "avg_launch_ms": (ms_f + ms_b) / max(n_f + n_b, 1),
-                "fwd_gbs": bytes_fwd * units * args.steps / 1e9 / (ms_f * 1e-3) if ms_f > 0 else None,
-                "bwd_gbs": bytes_bwd * units * args.steps / 1e9 / (ms_b * 1e-3) if ms_b > 0 else None,
+                "fwd_gbs": bytes_fwd * units * prof_steps / 1e9 / (ms_f * 1e-3) if ms_f > 0 else None,
+                "bwd_gbs": bytes_bwd * units * prof_steps / 1e9 / (ms_b * 1e-3) if ms_b > 0 else None,
                 "peak_source": f"{peaks['source']} HBM copy",
                 "algorithmic": "es*(2C+T) B/pixel fwd + es*3C B/pixel bwd"}
 
@@ -413,7 +439,10 @@ def run_native(args):
             "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
             "config": {"workload": workload, "l2": "256 MiB L2 flush between timed iterations",
-                       "timing": "CUDA events per step on the current stream, max over ranks"},
+                       "timing": "CUDA events per step on the current stream, max over ranks",
+                       "cuda_graph": {"value": graph is not None, "e2e": graph2 is not None},
+                       "roofline_timing": f"library CUDA events around the dominant kernels in an eager pass of "
+                                          f"{prof_steps} steps before the timed region"},
             "e2e": {"value": total_units / sec2, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "ms_per_step": sec2 * 1e3},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
@@ -431,6 +460,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--math", default=None, choices=["fp32", "f16", "bf16"])
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:

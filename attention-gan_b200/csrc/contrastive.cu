@@ -57,17 +57,28 @@ __global__ void ce_row_kernel(const float* __restrict__ raw, int B, const int32_
   }
 }
 
-// one thread per column b: lse over the rows (adjacent threads read adjacent columns)
-__global__ void ce_col_kernel(const float* __restrict__ raw, int B, const int32_t* __restrict__ cls,
-                              const int64_t* __restrict__ labels, float gamma3, float* __restrict__ lse_c,
-                              float* __restrict__ part_c) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+// one block per 32 columns, 32 x 8 threads: thread (tx, ty) folds rows ty, ty+8, ... of column tx
+// (adjacent threads read adjacent columns), then the 8 partial (max, sum) pairs are merged in order
+__global__ void __launch_bounds__(256)
+ce_col_kernel(const float* __restrict__ raw, int B, const int32_t* __restrict__ cls,
+              const int64_t* __restrict__ labels, float gamma3, float* __restrict__ lse_c,
+              float* __restrict__ part_c) {
+  __shared__ float ms[8][33], ss[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + tx;
   float m = -INFINITY, s = 0.f;
-  for (int a = 0; a < B; ++a) lse_push(m, s, logit_at(raw, cls, B, a, b, gamma3));
-  const float lse = m + logf(s);
-  lse_c[b] = lse;
-  part_c[b] = lse - logit_at(raw, cls, B, (int)labels[b], b, gamma3);
+  if (b < B)
+    for (int a = ty; a < B; a += 8) lse_push(m, s, logit_at(raw, cls, B, a, b, gamma3));
+  ms[ty][tx] = m;
+  ss[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && b < B) {
+    float M = -INFINITY, S = 0.f;
+    for (int k = 0; k < 8; ++k) lse_merge(M, S, ms[k][tx], ss[k][tx]);
+    const float lse = M + logf(S);
+    lse_c[b] = lse;
+    part_c[b] = lse - logit_at(raw, cls, B, (int)labels[b], b, gamma3);
+  }
 }
 
 __global__ void ce_loss_kernel(const float* __restrict__ part_r, const float* __restrict__ part_c, int B,
@@ -216,7 +227,7 @@ extern "C" int agb_contrastive_fwd(const float* raw, int B, const int32_t* class
   float* part_c = part_r + B;
   ce_row_kernel<<<B, 256, 0, st>>>(raw, B, class_ids, labels, gamma3, lse_r, part_r);
   if (int rc = check_launch("ce_row_kernel")) return rc;
-  ce_col_kernel<<<cdiv(B, 128), 128, 0, st>>>(raw, B, class_ids, labels, gamma3, lse_c, part_c);
+  ce_col_kernel<<<cdiv(B, 32), 256, 0, st>>>(raw, B, class_ids, labels, gamma3, lse_c, part_c);
   if (int rc = check_launch("ce_col_kernel")) return rc;
   ce_loss_kernel<<<1, 256, 0, st>>>(part_r, part_c, B, lambda, loss_out);
   if (int rc = check_launch("ce_loss_kernel")) return rc;

@@ -543,25 +543,88 @@ static int func_scores(const float* query, int64_t qs_b, int64_t qs_d, int64_t q
 }
 
 // beta of the matched pairs only (image b, caption row_offset + b), fp32: the att_maps output of
-// WordsLoss (words_loss.py:63) for the tensor-core path.  S, Bt: scratch [Bi,T,R] each.
+// WordsLoss (words_loss.py:63) for the tensor-core path.  One block per image, thread = region:
+// scores over the feature dim with the caption's words broadcast from shared memory, both softmaxes
+// in registers (S, Bt: unused scratch kept for ABI stability of the internal call).
+template <int TMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+diag_att_kernel(const float* __restrict__ img, const float* __restrict__ words, int64_t ws_b, int64_t ws_d,
+                int64_t ws_t, const int32_t* __restrict__ cap_lens, int T, int D, int R, float inv_sqrt_d,
+                float gamma1, int row_offset, float* __restrict__ att_out) {
+  extern __shared__ float w_s[];                  // [D][TMAX]
+  __shared__ float red_s[32 * TMAX];
+  __shared__ float z_s[TMAX];
+  const int b = blockIdx.x, r = threadIdx.x, i = row_offset + b;
+  const int L = min(max(cap_lens[i], 0), T);
+  for (int k = threadIdx.x; k < D * TMAX; k += blockDim.x) {
+    const int d = k / TMAX, t = k - d * TMAX;
+    w_s[k] = (t < L) ? words[(int64_t)i * ws_b + (int64_t)d * ws_d + (int64_t)t * ws_t] : 0.f;
+  }
+  __syncthreads();
+  const bool live = r < R;
+  float e[TMAX];
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) e[t] = 0.f;
+  if (live) {
+    const float* c = img + (size_t)b * D * R + r;
+    for (int d = 0; d < D; ++d) {
+      const float cv = c[(size_t)d * R];
+      const float4* w4 = reinterpret_cast<const float4*>(w_s + d * TMAX);
+#pragma unroll
+      for (int t4 = 0; t4 < TMAX / 4; ++t4) {
+        const float4 w = w4[t4];
+        e[4 * t4] = fmaf(cv, w.x, e[4 * t4]);
+        e[4 * t4 + 1] = fmaf(cv, w.y, e[4 * t4 + 1]);
+        e[4 * t4 + 2] = fmaf(cv, w.z, e[4 * t4 + 2]);
+        e[4 * t4 + 3] = fmaf(cv, w.w, e[4 * t4 + 3]);
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t)
+    if (t < L) {
+      e[t] *= inv_sqrt_d;
+      mx = fmaxf(mx, e[t]);
+    }
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t)
+    if (t < L) {
+      e[t] = __expf(e[t] - mx);
+      sum += e[t];
+    }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) e[t] = (t < L && live) ? __expf(gamma1 * (e[t] * inv)) : 0.f;
+  block_sum_words<TMAX>(e, L, red_s, z_s);
+  if (!live) return;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t)
+    if (t < T) att_out[((size_t)b * T + t) * R + r] = (t < L) ? e[t] / z_s[t] : 0.f;
+}
+
 int damsm_diag_att_maps(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                         const int32_t* cap_lens, int Bi, int T, int D, int R, float gamma1, int row_offset,
                         float* att_out, float* S, float* Bt, cudaStream_t st) {
-  SgemmArgs g{};
-  g.A = words + (int64_t)row_offset * ws_b; g.a_m = ws_t; g.a_k = ws_d; g.a_batch = ws_b;
-  g.B = img; g.b_k = R; g.b_n = 1; g.b_batch = (int64_t)D * R;
-  g.C = S; g.c_m = R; g.c_n = 1; g.c_batch = (int64_t)T * R;
-  g.M = T; g.N = R; g.K = D; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
-  if (int rc = sgemm_strided(g, Bi, st)) return rc;
+  (void)S;
+  (void)Bt;
   const int threads = (R + 31) / 32 * 32;
   const float isd = 1.f / sqrtf((float)D);
-  AGB_TMAX_SWITCH(pick_tmax(T), {
-    if (threads <= 352) pair_softmax_kernel<TMAX, 352><<<dim3(1, Bi), threads, 0, st>>>(
-        S, Bt, cap_lens, -1, T, T, R, isd, gamma1, row_offset, att_out);
-    else pair_softmax_kernel<TMAX, 1024><<<dim3(1, Bi), threads, 0, st>>>(
-        S, Bt, cap_lens, -1, T, T, R, isd, gamma1, row_offset, att_out);
+  const int tm = pick_tmax(T);
+  const size_t smem = (size_t)D * tm * sizeof(float);
+  AGB_TMAX_SWITCH(tm, {
+    if (threads <= 352) {
+      auto kern = diag_att_kernel<TMAX, 352>;
+      if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<Bi, threads, smem, st>>>(img, words, ws_b, ws_d, ws_t, cap_lens, T, D, R, isd, gamma1, row_offset, att_out);
+    } else {
+      auto kern = diag_att_kernel<TMAX, 1024>;
+      if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<Bi, threads, smem, st>>>(img, words, ws_b, ws_d, ws_t, cap_lens, T, D, R, isd, gamma1, row_offset, att_out);
+    }
   });
-  return check_launch("pair_softmax_kernel(diag)");
+  return check_launch("diag_att_kernel");
 }
 
 }  // namespace agb

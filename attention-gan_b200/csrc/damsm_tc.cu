@@ -231,7 +231,7 @@ struct TcPlan {
   // fused backward staging, per chunk of ct word tiles (N = ct*128 word rows) and all Bi images
   int ct;        // tiles per chunk
   int splits;    // slices of the image range in the d words GEMM
-  size_t off_E16, off_dV16, off_DS16, off_A116, off_dpp, off_dwp, off_m, total;
+  size_t off_E16, off_dV16, off_A116, off_dpp, off_dwp, off_m, total;
 };
 
 static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
@@ -250,7 +250,7 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_Ck = take((size_t)Bi * kD * kRCols * 2);
   p.off_attS = take((size_t)Bi * T * R * 4);
   p.off_attB = take((size_t)Bi * T * R * 4);
-  const size_t tile_bytes = (size_t)Bi * kTileN * (kRCols * 2 * 3 + kD * 2 + 4);
+  const size_t tile_bytes = (size_t)Bi * kTileN * (kRCols * 2 * 2 + kD * 2 + 4);
   size_t ct = ((size_t)8 << 30) / tile_bytes;
   if (ct < 1) ct = 1;
   if (ct > (size_t)p.nt_max) ct = p.nt_max;
@@ -259,7 +259,6 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   const size_t rows = (size_t)Bi * ct * kTileN;
   p.off_E16 = take(rows * kRCols * 2);
   p.off_dV16 = take(rows * kD * 2);
-  p.off_DS16 = take(rows * kRCols * 2);
   p.off_A116 = take(rows * kRCols * 2);
   p.off_dpp = take(rows * 4);
   p.off_dwp = take((size_t)p.splits * ct * kTileN * kD * 4);

@@ -46,6 +46,7 @@ struct TcGemmArgs {
   int MT;                      // 128-row output tiles per CTA (1 or 2), sharing the B operand
   int nsrc;                    // 1, or 2: a second (A2, B2) operand pair continues the same reduction
   int64_t a2_zrow, b2_zrow;    // batch row offsets of the second pair
+  int64_t a2_zcol, b2_zcol;    // batch column offsets of the second pair
 };
 int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st);
 int tc_gemm2(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapA2,

@@ -94,8 +94,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         unsigned char* sa = smem + s * stage_bytes;
         unsigned char* sb = sa + MT * kChunkBytes16;
         const int64_t azr = src ? g.a2_zrow : g.a_zrow, bzr = src ? g.b2_zrow : g.b_zrow;
-        const int arow = (int)(zb * azr + kb * g.a_kbrow), acol = (int)(zb * g.a_zcol + kb * g.a_kbcol);
-        const int brow = (int)(zb * bzr + kb * g.b_kbrow), bcol = (int)(zb * g.b_zcol + kb * g.b_kbcol);
+        const int64_t azc = src ? g.a2_zcol : g.a_zcol, bzc = src ? g.b2_zcol : g.b_zcol;
+        const int arow = (int)(zb * azr + kb * g.a_kbrow), acol = (int)(zb * azc + kb * g.a_kbcol);
+        const int brow = (int)(zb * bzr + kb * g.b_kbrow), bcol = (int)(zb * bzc + kb * g.b_kbcol);
         for (int mt = 0; mt < MT; ++mt) {
           unsigned char* sam = sa + mt * kChunkBytes16;
           const int mm = m0 + mt * 128;

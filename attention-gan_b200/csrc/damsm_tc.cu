@@ -157,42 +157,55 @@ template <typename T16> __device__ __forceinline__ uint16_t bits16(float v) {
   return *reinterpret_cast<const uint16_t*>(&h);
 }
 
-template <typename T16, int NL>
-__device__ __forceinline__ void caption_softmax(uint32_t taddr, int L, int off, int r, int R, uint32_t sE32,
-                                                float scale_log2, float g1_log2) {
-  float s[NL];
-  tmem_ld_n<NL>(taddr, s);
+// K region tiles at once (K = 2: the two score buffers of region tiles 0 and 1 are processed together,
+// which gives every thread two independent dependency chains to overlap MUFU / TMEM latencies)
+template <typename T16, int NL, int K>
+__device__ __forceinline__ void caption_softmax(const uint32_t (&taddr)[K], int L, int off, const int (&r)[K], int R,
+                                                uint32_t sE32, float scale_log2, float g1_log2) {
+  float s[K][NL];
+#pragma unroll
+  for (int k = 0; k < K; ++k) tmem_ld_n<NL>(taddr[k], s[k]);
   tmem_ld_wait();
-  if (r >= kRCols) return;
-  // element (row n, col r) of the K-major 128B-swizzled e tile: chunk (r>>6), 16-byte unit ((r&63)>>3) ^ (n&7)
-  const uint32_t colbase = sE32 + (uint32_t)(r >> 6) * kChunk + ((r & 7) << 1) + (uint32_t)off * 128;
-  const uint32_t x = ((r & 63) >> 3) << 4;
-  if (r >= R) {  // padding regions contribute nothing to V
+  uint32_t colbase[K], x[K];
+  bool store[K], live[K];
 #pragma unroll
-    for (int t = 0; t < NL; ++t)
-      if (t < NL - 4 || t < L) st_shared_u16(colbase + t * 128 + ((((off + t) << 4) & 0x70) ^ x), 0);
-    return;
+  for (int k = 0; k < K; ++k) {
+    // element (row n, col r) of the K-major 128B-swizzled e tile: chunk (r>>6), 16-byte unit ((r&63)>>3) ^ (n&7)
+    colbase[k] = sE32 + (uint32_t)(r[k] >> 6) * kChunk + ((r[k] & 7) << 1) + (uint32_t)off * 128;
+    x[k] = ((r[k] & 63) >> 3) << 4;
+    store[k] = r[k] < kRCols;
+    live[k] = r[k] < R;          // padding regions (R <= r < 320) contribute zeros to V
+  }
+  float ksc[K], mxs[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int t = NL - 4; t < NL; ++t)
+      if (t >= L) s[k][t] = -INFINITY;
+    float m4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m4[i] = s[k][i];
+#pragma unroll
+    for (int t = 4; t < NL; ++t) m4[t & 3] = fmaxf(m4[t & 3], s[k][t]);
+    mxs[k] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
   }
 #pragma unroll
-  for (int t = NL - 4; t < NL; ++t)
-    if (t >= L) s[t] = -INFINITY;
-  float m4[4];
+  for (int k = 0; k < K; ++k) {
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) m4[k] = s[k];
-#pragma unroll
-  for (int t = 4; t < NL; ++t) m4[t & 3] = fmaxf(m4[t & 3], s[t]);
-  const float mxs = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
-  float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int t = 0; t < NL; ++t) {
-    s[t] = exp2f(fmaf(s[t], scale_log2, -mxs));  // exp((s - max)/sqrt(D))
-    s4[t & 3] += s[t];
+    for (int t = 0; t < NL; ++t) {
+      s[k][t] = exp2f(fmaf(s[k][t], scale_log2, -mxs[k]));  // exp((s - max)/sqrt(D))
+      s4[t & 3] += s[k][t];
+    }
+    ksc[k] = g1_log2 / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
   }
-  const float k = g1_log2 / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
 #pragma unroll
-  for (int t = 0; t < NL; ++t) {
-    const uint16_t e = bits16<T16>(exp2f(s[t] * k));  // exp(gamma1 alpha)
-    if (t < NL - 4 || t < L) st_shared_u16(colbase + t * 128 + ((((off + t) << 4) & 0x70) ^ x), e);
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int t = 0; t < NL; ++t) {
+      const uint16_t e = live[k] ? bits16<T16>(exp2f(s[k][t] * ksc[k])) : (uint16_t)0;  // exp(gamma1 alpha)
+      if (store[k] && (t < NL - 4 || t < L)) st_shared_u16(colbase[k] + t * 128 + ((((off + t) << 4) & 0x70) ^ x[k]), e);
+    }
   }
 }
 

@@ -145,3 +145,54 @@ def test_tc_row_blocks_and_ragged_lengths(agb):
         assert torch.equal(mk, m[10 * k:10 * k + 10])
     ref = cf.words_similarity_fwd(img.numpy().reshape(B, 256, -1)[:6], wrd.numpy(), lens.numpy())
     assert np.abs(m[:6].double().cpu().numpy() - ref).max() < 2e-3
+
+
+@pytest.mark.parametrize("hw,T,B", [(8, 18, 9), (13, 7, 10), (16, 32, 6), (17, 5, 33), (4, 18, 5)])
+def test_tc_other_region_counts_and_lengths(agb, hw, T, B):
+    """R = 64 / 169 / 256 / 289 / 16 regions (1, 2, 2, 3, 1 region tiles), T up to the compiled limit 32"""
+    img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, T=T, hw=hw, seed=300 + hw + T, n_classes=4)
+    R = hw * hw
+    wl0, _, dc0, dw0 = cf.words_loss_fwd_bwd(img.numpy().reshape(B, 256, R), wrd.numpy(), labels.numpy(),
+                                             lens.numpy(), cls)
+    im = img.cuda().requires_grad_(True)
+    wd = wrd.cuda().requires_grad_(True)
+    wl, maps = agb.WordsLoss("cuda", math="f16").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
+    assert abs(wl.item() - wl0) <= 1e-3 * abs(wl0), (wl.item(), wl0)
+    assert maps[0].shape == (1, int(lens[0]), hw, hw)
+    wl.backward()
+    assert _rel(im.grad, dc0.reshape(img.shape)) < 5e-3
+    assert _rel(wd.grad, dw0) < 5e-3
+
+
+def test_tc_rectangular_block_with_row_offset_and_upstream_scale(agb):
+    """Bi != Bc (a rank's row block), explicit upstream gradient scale, frozen words (no dwords)"""
+    from agb_native import native, ops
+    B, Bi, r0 = 24, 8, 8
+    img, wrd, _, _, _, lens, _ = rp.synth_damsm(B, seed=77)
+    c = img.numpy().reshape(B, 256, -1)[r0:r0 + Bi]
+    g = torch.Generator().manual_seed(3)
+    dm = torch.randn(Bi, B, generator=g) * 0.05
+    dc0, dw0 = cf.words_similarity_bwd(c, wrd.numpy(), lens.numpy(), dm.numpy() * 0.5)
+    img3 = torch.from_numpy(c).float().cuda().contiguous()
+    l32 = lens.cuda().to(torch.int32)
+    m, att, _ = ops.damsm_fwd(img3, wrd.cuda(), l32, 4.0, 5.0, 1e-8, r0, True, native.AGB_MATH_TC_F16)
+    ref = cf.words_similarity_fwd(c, wrd.numpy(), lens.numpy())
+    assert np.abs(m.double().cpu().numpy() - ref).max() < 2e-3
+    gs = torch.tensor([0.5], device="cuda")
+    dimg, dwords = ops.damsm_bwd(img3, wrd.cuda(), l32, 4.0, 5.0, 1e-8, dm.cuda(), gs, True, native.AGB_MATH_TC_F16, m)
+    assert _rel(dimg, dc0) < 5e-3
+    assert _rel(dwords.transpose(1, 2), dw0) < 5e-3
+    # without the forward's m and without dwords
+    dimg2, none = ops.damsm_bwd(img3, wrd.cuda(), l32, 4.0, 5.0, 1e-8, dm.cuda(), gs, False, native.AGB_MATH_TC_F16)
+    assert none is None and _rel(dimg2, dc0) < 5e-3
+
+
+def test_tc_unsupported_shapes_fail_loudly(agb):
+    from agb_native import native, ops
+    assert not ops.damsm_supported(33, 256, 289, native.AGB_MATH_TC_F16)       # T > 32
+    assert not ops.damsm_supported(18, 128, 289, native.AGB_MATH_TC_F16)       # D != 256
+    assert not ops.damsm_supported(18, 256, 361, native.AGB_MATH_TC_F16)       # R > 320
+    with pytest.raises(native.NativeError):
+        ops.damsm_fwd(torch.zeros(2, 128, 289, device="cuda"), torch.zeros(2, 128, 18, device="cuda"),
+                      torch.full((2,), 18, dtype=torch.int32, device="cuda"), 4.0, 5.0, 1e-8, 0, False,
+                      native.AGB_MATH_TC_F16)

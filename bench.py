@@ -37,6 +37,15 @@ R_, T_, D_ = 289, 18, 256
 L2_FLUSH_BYTES = 256 << 20
 
 
+def load_traffic(workload):
+    """measured DRAM bytes per step of the dominant kernels (committed ncu capture), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
+            return json.load(fh)[workload]["bytes_per_step"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -406,7 +415,8 @@ def run_native(args):
         ach = flops / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
         peak = peaks["tf_burst"]
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "kernel": "damsm_tc_fwd/bwd (tcgen05)" if tc else "sgemm_strided_kernel (fp32 CUDA cores)",
+                "traffic": load_traffic(args.workload) if (tc and args.batch is None) else None,
+                "kernel": "damsm_fwd2_kernel + damsm_bwd2_kernel + tc_gemm_kernel (tcgen05)" if tc else "sgemm_strided_kernel (fp32 CUDA cores)",
                 "launches": int(n_l), "avg_launch_ms": ms_tot / max(n_l, 1),
                 "peak_source": f"{peaks['source']} bf16 burst (kernels timed one by one with events)",
                 "algorithmic": "12*R*mean(cap_len)*D flop per (image,caption) pair, fwd+bwd"}
@@ -415,7 +425,8 @@ def run_native(args):
         gb = (bytes_fwd + bytes_bwd) * units * prof_steps / 1e9
         ach = gb / ((ms_f + ms_b) * 1e-3) if ms_f + ms_b > 0 else 0.0
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                "traffic": None, "kernel": "word_attn_fwd_kernel + word_attn_bwd_kernel",
+                "traffic": load_traffic(args.workload) if args.batch is None else None,
+                "kernel": "word_attn_fwd(_tc)_kernel + word_attn_bwd(_tc)_kernel",
                 "launches": int(n_f + n_b), "avg_launch_ms": (ms_f + ms_b) / max(n_f + n_b, 1),
                 "fwd_gbs": bytes_fwd * units * prof_steps / 1e9 / (ms_f * 1e-3) if ms_f > 0 else None,
                 "bwd_gbs": bytes_bwd * units * prof_steps / 1e9 / (ms_b * 1e-3) if ms_b > 0 else None,

@@ -114,6 +114,70 @@ __global__ void ce_grad_kernel(const float* __restrict__ raw, int B, const int32
   draw[(size_t)blockIdx.y * B + b] = d;
 }
 
+// Whole two-way CE in one CTA for B <= 128 (the reference's batch sizes: 16-64): logits live in
+// shared memory, warp w folds rows w, w+8, ... and then columns w, w+8, ... with the same in-order
+// merges as the multi-kernel path, loss and the requested gradient rows come out of the same launch.
+__global__ void __launch_bounds__(256)
+ce_small_kernel(const float* __restrict__ raw, int B, const int32_t* __restrict__ cls,
+                const int64_t* __restrict__ labels, float gamma3, float lambda, int row_begin, int row_count,
+                float* __restrict__ loss_out, float* __restrict__ draw) {
+  extern __shared__ float lg[];                 // [B][B+1] logits
+  __shared__ float lse_r[128], lse_c[128], part[256];
+  const int P = B + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
+    const int a = i / B, b = i - a * B;
+    lg[a * P + b] = logit_at(raw, cls, B, a, b, gamma3);
+  }
+  __syncthreads();
+  for (int a = warp; a < B; a += 8) {           // rows
+    float m = -INFINITY, s = 0.f;
+    for (int b = lane; b < B; b += 32) lse_push(m, s, lg[a * P + b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m, s, m2, s2);
+    }
+    if (lane == 0) {
+      lse_r[a] = m + logf(s);
+      part[a] = lse_r[a] - lg[a * P + (int)labels[a]];
+    }
+  }
+  for (int b = warp; b < B; b += 8) {           // columns
+    float m = -INFINITY, s = 0.f;
+    for (int a = lane; a < B; a += 32) lse_push(m, s, lg[a * P + b]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m, s, m2, s2);
+    }
+    if (lane == 0) {
+      lse_c[b] = m + logf(s);
+      part[128 + b] = lse_c[b] - lg[(int)labels[b] * P + b];
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float acc = 0.f;
+    for (int i = lane; i < B; i += 32) acc += part[i] + part[128 + i];
+    acc = warp_sum(acc);
+    if (lane == 0) loss_out[0] = lambda * acc / (float)B;
+  }
+  if (draw != nullptr) {
+    for (int i = threadIdx.x; i < row_count * B; i += blockDim.x) {
+      const int ra = i / B, b = i - ra * B, a = row_begin + ra;
+      const float l = lg[a * P + b];
+      float d = 0.f;
+      if (l != -INFINITY) {
+        d = __expf(l - lse_r[a]) + __expf(l - lse_c[b]);
+        if ((int)labels[a] == b) d -= 1.f;
+        if ((int)labels[b] == a) d -= 1.f;
+        d *= lambda * gamma3 / (float)B;
+      }
+      draw[i] = d;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // sentence cosine matrix                                              sentence_loss.py:33-38
 // MODE 0: scos[b,i] = <c_b,r_i> / max(|c_b||r_i|, eps)
@@ -168,38 +232,70 @@ sent_cos_kernel(const float* __restrict__ cnn, const float* __restrict__ rnn, in
   }
 }
 
-// x[v,:] -= (sum_j gn[v,j] or sum_j gn[j,v]) / |y_v|^2 * y[v,:]
-__global__ void sent_norm_term_kernel(float* __restrict__ dx, const float* __restrict__ x,
-                                      const float* __restrict__ gn, int n_sum, int64_t stride_v,
-                                      int64_t stride_j, int D) {
-  const int v = blockIdx.x;
-  __shared__ float red[32];
-  __shared__ float coef_s;
-  float acc = 0.f, ss = 0.f;
-  for (int j = threadIdx.x; j < n_sum; j += blockDim.x) acc += gn[(int64_t)v * stride_v + (int64_t)j * stride_j];
+// Gradient of the cosine matrix w.r.t. one side, one block per row v of x (x = cnn for SIDE 0, rnn for
+// SIDE 1; y is the other side, n_y rows):
+//   g_j = dscos[v,j] * gs / max(|x_v||y_j|, eps),   dx_v = sum_j g_j y_j - (sum_j [clamp inactive] g_j <x_v,y_j>) / |x_v|^2 x_v
+// The dots are recomputed here (B^2 D flop, negligible) so no workspace and no second launch is needed.
+template <int SIDE>
+__global__ void __launch_bounds__(256)
+sent_grad_kernel(const float* __restrict__ x, const float* __restrict__ y, int n_x, int n_y, int D, float eps,
+                 const float* __restrict__ dscos, const float* __restrict__ gscale, float* __restrict__ dx) {
+  extern __shared__ float sm[];                 // x_v [D] | g [n_y]
+  float* x_s = sm;
+  float* g_s = sm + D;
+  __shared__ float red[8];
+  __shared__ float p2_s, gn_s;
+  const int v = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ss = 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float t = x[(size_t)v * D + d];
+    x_s[d] = t;
     ss = fmaf(t, t, ss);
   }
-  acc = warp_sum(acc);
   ss = warp_sum(ss);
-  const int nw = (blockDim.x + 31) / 32;
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  float tot = 0.f;
-  if (threadIdx.x == 0)
-    for (int w = 0; w < nw; ++w) tot += red[w];
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  if (lane == 0) red[warp] = ss;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float n2 = 0.f;
-    for (int w = 0; w < nw; ++w) n2 += red[w];
-    coef_s = n2 > 0.f ? tot / n2 : 0.f;
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    p2_s = t;
   }
   __syncthreads();
-  const float coef = coef_s;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) dx[(size_t)v * D + d] -= coef * x[(size_t)v * D + d];
+  const float p = sqrtf(p2_s);
+  const float gs = gscale ? *gscale : 1.f;
+  float gn = 0.f;
+  for (int j = warp; j < n_y; j += 8) {
+    float num = 0.f, q2 = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float r = y[(size_t)j * D + d];
+      num = fmaf(x_s[d], r, num);
+      q2 = fmaf(r, r, q2);
+    }
+    num = warp_sum(num);
+    q2 = warp_sum(q2);
+    if (lane == 0) {
+      const float pq = p * sqrtf(q2);
+      const float up = SIDE == 0 ? dscos[(size_t)v * n_y + j] : dscos[(size_t)j * n_x + v];
+      const float g = up * gs / fmaxf(pq, eps);
+      g_s[j] = g;
+      if (pq > eps) gn += g * num;
+    }
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = gn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    gn_s = p2_s > 0.f ? t / p2_s : 0.f;
+  }
+  __syncthreads();
+  const float coef = gn_s;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < n_y; ++j) acc = fmaf(g_s[j], y[(size_t)j * D + d], acc);
+    dx[(size_t)v * D + d] = acc - coef * x_s[d];
+  }
 }
 
 }  // namespace agb
@@ -221,6 +317,13 @@ extern "C" int agb_contrastive_fwd(const float* raw, int B, const int32_t* class
   if (draw && (row_begin < 0 || row_count < 0 || row_begin + row_count > B)) return fail_arg("bad row range [%d,+%d) of %d", row_begin, row_count, B);
   if (row_count > 65535) return fail_unsupported("row_count=%d > 65535", row_count);
   cudaStream_t st = (cudaStream_t)stream;
+  if (B <= 128) {
+    const size_t smem = (size_t)B * (B + 1) * sizeof(float);
+    if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(ce_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ce_small_kernel<<<1, 256, smem, st>>>(raw, B, class_ids, labels, gamma3, lambda, row_begin, row_count, loss_out,
+                                          row_count > 0 ? draw : nullptr);
+    return check_launch("ce_small_kernel");
+  }
   float* lse_r = (float*)workspace;
   float* lse_c = lse_r + B;
   float* part_r = lse_c + B;
@@ -256,39 +359,31 @@ extern "C" int agb_sent_cos_fwd(const float* cnn, const float* rnn, int Bi, int 
 }
 
 extern "C" size_t agb_sent_cos_bwd_workspace_bytes(int Bi, int Bc) {
-  return (Bi > 0 && Bc > 0) ? (size_t)2 * Bi * Bc * sizeof(float) : 0;
+  (void)Bi;
+  (void)Bc;
+  return 0;   // kept for ABI stability: the backward kernels recompute what they need
 }
 
 extern "C" int agb_sent_cos_bwd(const float* cnn, const float* rnn, int Bi, int Bc, int D, float eps,
                                 const float* dscos, const float* gscale, float* dcnn, float* drnn,
                                 void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
   if (Bi <= 0 || Bc <= 0 || D <= 0) return fail_arg("non-positive size");
-  if (D > 8192) return fail_unsupported("D=%d > 8192", D);
-  if (!cnn || !rnn || !dscos || !workspace) return fail_arg("null pointer");
-  if (workspace_bytes < agb_sent_cos_bwd_workspace_bytes(Bi, Bc)) {
-    set_error("workspace too small");
-    return AGB_E_WORKSPACE;
-  }
+  if (D > 8192 || Bi > 8192 || Bc > 8192) return fail_unsupported("D=%d Bi=%d Bc=%d exceed 8192", D, Bi, Bc);
+  if (!cnn || !rnn || !dscos) return fail_arg("null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  float* g = (float*)workspace;
-  float* gn = g + (size_t)Bi * Bc;
-  sent_cos_kernel<1><<<Bi, 256, (size_t)D * sizeof(float), st>>>(cnn, rnn, Bc, D, eps, g, gn, dscos, gscale);
-  if (int rc = check_launch("sent_cos_kernel<1>")) return rc;
-  if (dcnn) {  // dcnn = g rnn - rowsum(gn)/|c|^2 c
-    SgemmArgs a{};
-    a.A = g; a.a_m = Bc; a.a_k = 1; a.B = rnn; a.b_k = D; a.b_n = 1; a.C = dcnn; a.c_m = D; a.c_n = 1;
-    a.M = Bi; a.N = D; a.K = Bc; a.KB = 1; a.alpha = 1.f; a.accumulate = 0;
-    if (int rc = sgemm_strided(a, 1, st)) return rc;
-    sent_norm_term_kernel<<<Bi, 128, 0, st>>>(dcnn, cnn, gn, Bc, Bc, 1, D);
-    if (int rc = check_launch("sent_norm_term_kernel")) return rc;
+  if (dcnn) {   // dcnn[b] = sum_i g[b,i] r_i - (...) c_b
+    const size_t smem = (size_t)(D + Bc) * sizeof(float);
+    if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(sent_grad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sent_grad_kernel<0><<<Bi, 256, smem, st>>>(cnn, rnn, Bi, Bc, D, eps, dscos, gscale, dcnn);
+    if (int rc = check_launch("sent_grad_kernel<0>")) return rc;
   }
-  if (drnn) {  // drnn = g^T cnn - colsum(gn)/|r|^2 r   (partial over the local images when sharded)
-    SgemmArgs a{};
-    a.A = g; a.a_m = 1; a.a_k = Bc; a.B = cnn; a.b_k = D; a.b_n = 1; a.C = drnn; a.c_m = D; a.c_n = 1;
-    a.M = Bc; a.N = D; a.K = Bi; a.KB = 1; a.alpha = 1.f; a.accumulate = 0;
-    if (int rc = sgemm_strided(a, 1, st)) return rc;
-    sent_norm_term_kernel<<<Bc, 128, 0, st>>>(drnn, rnn, gn, Bi, 1, Bc, D);
-    if (int rc = check_launch("sent_norm_term_kernel")) return rc;
+  if (drnn) {   // drnn[i] = sum_b g[b,i] c_b - (...) r_i   (partial over the local images when sharded)
+    const size_t smem = (size_t)(D + Bi) * sizeof(float);
+    if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(sent_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sent_grad_kernel<1><<<Bc, 256, smem, st>>>(rnn, cnn, Bc, Bi, D, eps, dscos, gscale, drnn);
+    if (int rc = check_launch("sent_grad_kernel<1>")) return rc;
   }
   return 0;
 }

@@ -158,6 +158,87 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
   else if constexpr (NL >= 8) { tmem_ld8(taddr, v); if constexpr (NL > 8) tmem_ld_n<NL - 8>(taddr + 8, v + 8); }
   else tmem_ld4(taddr, v);
 }
+// ---- fragment-layout TMEM access (16 lanes per instruction) -------------------------------------
+// tcgen05.ld.16x256b.xN: thread i of the warp receives, for column block k < N (8 fp32 columns
+// each), rows (i/4) and (i/4 + 8) of the 16 lanes at `taddr`, columns 8k + 2(i%4) + {0,1}:
+//   v[4k + 0], v[4k + 1] = row i/4,     cols 8k + 2(i%4), +1
+//   v[4k + 2], v[4k + 3] = row i/4 + 8, same columns
+// i.e. the mma accumulator fragment layout, so a packed 16-bit pair per (row, column pair) can go
+// straight to stmatrix.trans (transposed 16-byte rows in shared memory) or back into TMEM as a
+// 16-bit A operand with tcgen05.st.16x128b (32-bit column 4k + i%4 of the same rows).
+__device__ __forceinline__ void tmem_ldf1(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ldf2(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ldf4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// KB column blocks of 8 (KB <= 8) -> v[4*KB]
+template <int KB>
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, float* v) {
+  if constexpr (KB >= 4) { tmem_ldf4(taddr, v); if constexpr (KB > 4) tmem_ld_frag<KB - 4>(taddr + 32, v + 16); }
+  else if constexpr (KB >= 2) { tmem_ldf2(taddr, v); if constexpr (KB > 2) tmem_ld_frag<KB - 2>(taddr + 16, v + 8); }
+  else tmem_ldf1(taddr, v);
+}
+// tcgen05.st.16x128b.xN: r[2k + j] = 32-bit column 4k + i%4 of row i/4 + 8j (16 lanes at taddr)
+__device__ __forceinline__ void tmem_stf2(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x2.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_stf4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_stf8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// four 8x8 16-bit matrices, transposed: thread i supplies the address of the 16-byte row (i%8) of
+// matrix (i/8); register m holds elements [2(i%4)+{0,1}][i/4] of stored matrix m
+__device__ __forceinline__ void stsm_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};"
+               ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
+// PB blocks of 4 32-bit columns (PB in {2, 4, 6, 8}) from r[2 * PB]
+template <int PB>
+__device__ __forceinline__ void tmem_st_frag(uint32_t taddr, const uint32_t* r) {
+  if constexpr (PB >= 8) tmem_stf8(taddr, r);
+  else if constexpr (PB >= 4) { tmem_stf4(taddr, r); if constexpr (PB > 4) tmem_st_frag<PB - 4>(taddr + 16, r + 8); }
+  else tmem_stf2(taddr, r);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+template <typename T16> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }

@@ -68,18 +68,84 @@ struct AttnFwdParams {
 };
 
 constexpr int kAttnStages = 3;
+constexpr uint32_t kHalfLanes = 16u << 16;      // TMEM address of the second 16 lanes of a warp's quarter
 
-// load TL (multiple of 8, <= 64) consecutive TMEM columns of this thread's lane
-template <int TL>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
-  if constexpr (TL >= 32) {
-    tmem_ld32(taddr, v);
-    if constexpr (TL > 32) tmem_ld_cols<TL - 32>(taddr + 32, v + 32);
-  } else if constexpr (TL >= 16) {
-    tmem_ld16(taddr, v);
-    if constexpr (TL > 16) tmem_ld_cols<TL - 16>(taddr + 16, v + 16);
-  } else {
-    tmem_ld8(taddr, v);
+// Epilogue layout (both kernels).  The epilogue warps read TMEM in the 16x256b fragment layout
+// (tc_common.cuh): thread i of warp q owns the pixels q*32 + 16h + 8j + i/4 (h, j in {0,1}) and,
+// per block k of 8 columns, the column pair 8k + 2(i%4) + {0,1}.  A softmax over the words is a
+// reduction inside the thread plus two xor-shuffles over the quad.  Every 16-bit output is packed
+// as one register per (pixel, column pair), which is exactly what
+//   * tcgen05.st.16x128b needs to put P / ds back into TMEM as the A operand of the next GEMM, and
+//   * stmatrix.trans needs to lay [column][8 pixels] 16-byte rows into shared memory, from where
+//     the warp copies whole 64-byte row segments to global memory with 128-bit accesses
+// so the epilogue issues ~1 instruction per 2 outputs instead of ~4 per output.
+// Masked words get their -inf through the tensor core: an extra K = 16 block whose A operand is a
+// constant (k = 0 row of ones) and whose B operand holds 0 / -inf per word.
+
+// per-warp staging geometry inside a [rows x 128 px] tile stored as two swizzled [rows x 64 px] boxes
+struct StageAddr {
+  uint32_t st;      // stmatrix row address of this lane for row block 0 (add 1024 per block of 8 rows)
+  uint32_t ld;      // ld.shared address of this lane's 16-byte chunk for row block 0
+  int row, pxc;     // row (0..7) and pixel offset (multiple of 8, relative to the tile) of that chunk
+};
+__device__ __forceinline__ StageAddr stage_addr(uint32_t base, int rows, int q, int lane) {
+  StageAddr a;
+  const uint32_t box = base + (uint32_t)(q >> 1) * (uint32_t)(rows * 128);
+  const int sr = lane & 7, sm = lane >> 3;
+  a.st = box + sr * 128 + (((((q & 1) << 2) + sm) ^ sr) << 4);
+  a.row = lane >> 2;
+  const int cq = lane & 3;
+  a.ld = box + a.row * 128 + (((((q & 1) << 2) + cq) ^ (a.row & 7)) << 4);
+  a.pxc = q * 32 + cq * 8;
+  return a;
+}
+
+// softmax over the KB*8 columns of the four pixel rows a thread owns; v[h][4k + 2j + e]
+template <int KB>
+__device__ __forceinline__ void frag_softmax(float (&v)[2][4 * KB]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float mx = fmaxf(v[h][2 * j], v[h][2 * j + 1]);
+#pragma unroll
+      for (int k = 1; k < KB; ++k) mx = fmaxf(mx, fmaxf(v[h][4 * k + 2 * j], v[h][4 * k + 2 * j + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KB; ++k)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float x = exp2f(v[h][4 * k + 2 * j + e] - mx);   // all masked: (-inf) - (-inf) = NaN, like the reference
+          v[h][4 * k + 2 * j + e] = x;
+          sum += x;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = __fdividef(1.f, sum);
+#pragma unroll
+      for (int k = 0; k < KB; ++k)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) v[h][4 * k + 2 * j + e] *= inv;
+    }
+}
+
+// constant operands of the mask-bias MMA: sOnes = MN-major [16 k][128 px] (two 64-px halves, 2 KB
+// apart) with k = 0 all ones; sBias = K-major [NT words][64 k] with k = 0 holding 0 or -inf
+template <typename IO>
+__device__ __forceinline__ void fill_mask_operands(unsigned char* sOnes, unsigned char* sBias, int NT,
+                                                   const int64_t* mask_b, int T) {
+  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) {
+    const int row = (i >> 3) & 15;       // 16 rows of 128 B per half
+    const uint32_t one2 = pack2<IO>(1.f, 1.f);
+    reinterpret_cast<uint4*>(sOnes)[i] = row == 0 ? make_uint4(one2, one2, one2, one2) : make_uint4(0, 0, 0, 0);
+  }
+  for (int i = threadIdx.x; i < NT * 128 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sBias)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NT; t += blockDim.x) {
+    const bool keep = t < T && mask_b[t] != 0;
+    *reinterpret_cast<IO*>(sBias + sw128_off(t, 0)) = f2h<IO>(keep ? 0.f : -INFINITY);
   }
 }
 
@@ -87,6 +153,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
 template <typename IO, int NT, int TL>
 __global__ void __launch_bounds__(192)
 word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdParams p) {
+  constexpr int KB = TL / 8;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int C = p.C;
@@ -96,7 +163,11 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
   unsigned char* sB1hi = smem + kAttnStages * stage_bytes;   // [NT rows t][64 k=c]  io type
   unsigned char* sB1lo = sB1hi + NT * 128;
   unsigned char* sB2hi = sB1lo + NT * 128;                   // [C rows c][64 k=t]   fp16
-  unsigned char* sB2lo = sB2hi + 64 * 128;
+  unsigned char* sB2lo = sB2hi + box_bytes;
+  unsigned char* sOnes = sB2lo + box_bytes;                  // 4 KB
+  unsigned char* sBias = sOnes + 4096;                       // [NT rows t][64 k]
+  unsigned char* sStA = sBias + NT * 128;                    // attn staging: 2 boxes x [TL rows][64 px]
+  unsigned char* sStC = sStA + 2 * TL * 128;                 // ctx staging:  2 boxes x [C rows][64 px]
   __shared__ uint64_t h_full[kAttnStages], h_empty[kAttnStages], s_full[2], p_ready[2], c_full[2], c_empty[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -123,22 +194,23 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
   // B operands of both GEMMs from W.e of this sample: hi + lo 16-bit split, K-major swizzled rows
   {
     const float* we = p.we + (size_t)b * C * p.T;
-    for (int i = threadIdx.x; i < NT * 64; i += blockDim.x) {       // B1[t][c]
-      const int t = i >> 6, c = i & 63;
-      const float x = (t < p.T && c < C) ? we[c * p.T + t] * p.qscale : 0.f;
+    for (int i = threadIdx.x; i < NT * C; i += blockDim.x) {        // B1[t][c]
+      const int t = i / C, c = i - t * C;
+      const float x = t < p.T ? we[c * p.T + t] * p.qscale : 0.f;
       const IO hi = f2h<IO>(x);
       const IO lo = f2h<IO>(x - to_f32(hi));
       *reinterpret_cast<IO*>(sB1hi + sw128_off(t, c)) = hi;
       *reinterpret_cast<IO*>(sB1lo + sw128_off(t, c)) = lo;
     }
-    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {       // B2[c][t]
-      const int c = i >> 6, t = i & 63;
-      const float x = (t < p.T && c < C) ? we[c * p.T + t] : 0.f;
+    for (int i = threadIdx.x; i < C * NT; i += blockDim.x) {        // B2[c][t]
+      const int c = i / NT, t = i - c * NT;
+      const float x = t < p.T ? we[c * p.T + t] : 0.f;
       const __half hi = __float2half_rn(x);
       const __half lo = __float2half_rn(x - __half2float(hi));
       *reinterpret_cast<__half*>(sB2hi + sw128_off(c, t)) = hi;
       *reinterpret_cast<__half*>(sB2lo + sw128_off(c, t)) = lo;
     }
+    fill_mask_operands<IO>(sOnes, sBias, NT, p.mask + (size_t)b * p.T, p.T);
     fence_proxy_async();
   }
   tc_fence_before();
@@ -164,15 +236,18 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
     if (elect_one()) {
       const uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);   // A MN-major (pixels contiguous)
       const uint32_t idesc2 = make_idesc(128, C, 0);                       // P (TMEM) x W.e, fp16
-      const int ks1 = C >> 4, ks2 = NT >> 4;
+      const int ks1 = C >> 4, ks2 = (TL + 15) >> 4;
+      const uint64_t d_ones = make_desc_sw128_mn_lbo(smem_u32(sOnes), 2048u);
+      const uint64_t d_bias = make_desc_sw128(smem_u32(sBias));
       auto gemm1 = [&](int it) {
         const int s = it % kAttnStages, use = it / kAttnStages, u = it & 1;
         mbar_wait(&h_full[s], use & 1);
         tc_fence_after();
         const uint32_t a0 = smem_u32(sH + s * stage_bytes);
+        umma_f16(tmem + u * bufc, d_ones, d_bias, idesc1, 0u);            // S = 0 / -inf per word
         for (int kk = 0; kk < ks1; ++kk) {
           const uint64_t da = make_desc_sw128_mn_lbo(a0 + kk * 2048, (uint32_t)box_bytes);
-          umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1hi)) + 2 * kk, idesc1, kk ? 1u : 0u);
+          umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1hi)) + 2 * kk, idesc1, 1u);
           umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1lo)) + 2 * kk, idesc1, 1u);
         }
         umma_commit(&h_empty[s]);
@@ -195,80 +270,88 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
       }
     }
   } else {
-    // ===================== epilogue: thread = pixel =====================
+    // ===================== epilogue (fragment layout, see above) =====================
     const int q = warp & 3;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int px = q * 32 + lane;
-    uint64_t valid = 0;
-    for (int t = 0; t < p.T; ++t)
-      if (p.mask[(size_t)b * p.T + t] != 0) valid |= 1ull << t;
+    const uint32_t lane0 = (uint32_t)(q * 32) << 16;
     IO* ctx = (IO*)p.ctx + (size_t)b * p.ctx_bs;
     IO* attn = p.attn ? (IO*)p.attn + (size_t)b * p.T * p.HW : nullptr;
+    const StageAddr sa = stage_addr(smem_u32(sStA), TL, q, lane);
+    const StageAddr sc = stage_addr(smem_u32(sStC), C, q, lane);
+    const size_t row8 = (size_t)8 * p.HW;
 
     auto softmax_phase = [&](int it) {
       const int u = it & 1, k = it >> 1;
-      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
       mbar_wait(&s_full[u], k & 1);
       tc_fence_after();
-      float s[TL];
-      tmem_ld_cols<TL>(tmem + lane_addr + u * bufc, s);
+      float v[2][4 * KB];
+      tmem_ld_frag<KB>(tmem + lane0 + u * bufc, v[0]);
+      tmem_ld_frag<KB>(tmem + lane0 + kHalfLanes + u * bufc, v[1]);
       tmem_ld_wait();
-      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      frag_softmax<KB>(v);
+      constexpr int PB = 2 * ((TL + 15) / 16);   // column blocks of 8 words GEMM2 reads (K = 16 per step)
+      uint32_t pk[2][2 * PB];
 #pragma unroll
-      for (int t = 0; t < TL; ++t) {
-        if (!((valid >> t) & 1)) s[t] = -INFINITY;
-        m4[t & 3] = fmaxf(m4[t & 3], s[t]);
-      }
-      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int t = 0; t < TL; ++t) {
-        s[t] = exp2f(s[t] - mx);           // all-masked sample: (-inf) - (-inf) = NaN, like the reference
-        s4[t & 3] += s[t];
-      }
-      const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-      uint32_t pk[NT / 2];
+        for (int kk = 0; kk < PB; ++kk)
 #pragma unroll
-      for (int t = 0; t < NT; t += 2) {
-        if (t < TL) {
-          const float a0 = s[t] * inv, a1 = s[t + 1] * inv;
-          s[t] = a0;
-          s[t + 1] = a1;
-          const __half2 h2 = __floats2half2_rn(a0, a1);
-          pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h2);
-        } else {
-          pk[t / 2] = 0u;
-        }
-      }
-      tmem_st16(tmem + lane_addr + u * bufc, pk);
-      if constexpr (NT == 64) tmem_st16(tmem + lane_addr + u * bufc + 16, pk + 16);
+          for (int j = 0; j < 2; ++j)
+            pk[h][2 * kk + j] = kk < KB ? pack2<__half>(v[h][4 * kk + 2 * j], v[h][4 * kk + 2 * j + 1]) : 0u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * bufc, pk[h]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[u]);
-      if (attn != nullptr && pix < p.HW) {
+      if (attn != nullptr) {
 #pragma unroll
-        for (int t = 0; t < TL; ++t)
-          if (t < p.T) attn[(size_t)t * p.HW + pix] = f2h<IO>(s[t]);
+        for (int kk = 0; kk < KB; ++kk) {
+          uint32_t r[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if constexpr (std::is_same<IO, __half>::value) r[m] = pk[m >> 1][2 * kk + (m & 1)];
+            else r[m] = pack2<IO>(v[m >> 1][4 * kk + 2 * (m & 1)], v[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+          }
+          stsm_x4_trans(sa.st + kk * 1024, r[0], r[1], r[2], r[3]);
+        }
+        __syncwarp();
+        const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + sa.pxc;
+        IO* dst = attn + (size_t)sa.row * p.HW + pix;
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+          if (sa.row + 8 * i < p.T && pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sa.ld + i * 1024);
+          dst += row8;
+        }
+        __syncwarp();
       }
     };
     auto context_phase = [&](int it) {
       const int u = it & 1, k = it >> 1;
-      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
       mbar_wait(&c_full[u], k & 1);
       tc_fence_after();
       for (int c0 = 0; c0 < C; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + lane_addr + u * bufc + NT + c0, v);
+        float w[2][8];
+        tmem_ldf2(tmem + lane0 + u * bufc + NT + c0, w[0]);
+        tmem_ldf2(tmem + lane0 + kHalfLanes + u * bufc + NT + c0, w[1]);
         tmem_ld_wait();
-        if (pix < p.HW) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ctx[(size_t)(c0 + j) * p.HW + pix] = f2h<IO>(v[j]);
+        for (int kk = 0; kk < 2; ++kk) {
+          uint32_t r[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+          stsm_x4_trans(sc.st + (c0 / 8 + kk) * 1024, r[0], r[1], r[2], r[3]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&c_empty[u]);
+      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + sc.pxc;
+      IO* dst = ctx + (size_t)sc.row * p.HW + pix;
+      for (int i = 0; i < C / 8; ++i) {
+        if (pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sc.ld + i * 1024);
+        dst += row8;
+      }
+      __syncwarp();
     };
     for (int it = 0; it < ntile; ++it) {
       softmax_phase(it);
@@ -288,7 +371,9 @@ static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaSt
                             std::is_same<IO, __nv_bfloat16>::value))
     return rc;
   const int NT = p.T <= 32 ? 32 : 64;
-  const int smem = kAttnStages * 2 * p.C * 128 + 2 * NT * 128 + 2 * 64 * 128 + 1024;
+  const int TL = (p.T + 7) / 8 * 8;
+  const int smem = kAttnStages * 2 * p.C * 128 + 2 * NT * 128 + 2 * p.C * 128 + 4096 + NT * 128 + 2 * TL * 128 +
+                   2 * p.C * 128 + 1024;
   dim3 grid(p.ctas_per_sample, p.B);
   const int slot = prof_begin(PROF_ATTN_FWD, st);
 #define AGB_ATTN_FWD_CASE(NTV, TLV)                                                              \
@@ -346,6 +431,7 @@ __global__ void __launch_bounds__(192)
 word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapD,
                         const AttnBwdParams p) {
   constexpr int NT = kBwdNT;
+  constexpr int KB = TL / 8;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   const int C = p.C;
@@ -356,7 +442,10 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   unsigned char* sB1u = sB1s + 2 * NT * 128;                   // [t][c] unscaled       hi, lo (io type)
   unsigned char* sB2 = sB1u + 2 * NT * 128;                    // [c][t] * scale        hi, lo (bf16), 32 rows each
   unsigned char* sBt = sB2 + 2 * 32 * 128;                     // 2 buffers x 2 px-chunks x [2NT rows][64 px]
-  float* sAcc = reinterpret_cast<float*>(sBt + 2 * 2 * (2 * NT) * 128);   // [2][C][NT]
+  unsigned char* sOnes = sBt + 2 * 2 * (2 * NT) * 128;         // mask-bias MMA operands (see the forward kernel)
+  unsigned char* sBias = sOnes + 4096;
+  unsigned char* sStD = sBias + NT * 128;                      // dh staging: 2 boxes x [C rows][64 px]
+  float* sAcc = reinterpret_cast<float*>(sIn);                 // [2][C][NT], aliases the input ring after the last MMA
   __shared__ uint64_t in_full[kBwdStages], in_empty[kBwdStages], s_full[2], p_ready[2], dh_full[2], dh_empty[2], acc_done;
   __shared__ uint32_t tmem_base_s;
 
@@ -382,9 +471,9 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   {
     const float* we = p.we + (size_t)b * C * p.T;
     const float qs = p.scale * kLog2e;
-    for (int i = threadIdx.x; i < NT * 64; i += blockDim.x) {
-      const int t = i >> 6, c = i & 63;
-      const float w = (t < p.T && c < C) ? we[c * p.T + t] : 0.f;
+    for (int i = threadIdx.x; i < NT * C; i += blockDim.x) {
+      const int t = i / C, c = i - t * C;
+      const float w = t < p.T ? we[c * p.T + t] : 0.f;
       const float xs = w * qs;
       IO hi = f2h<IO>(xs);
       *reinterpret_cast<IO*>(sB1s + sw128_off(t, c)) = hi;
@@ -393,16 +482,17 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       *reinterpret_cast<IO*>(sB1u + sw128_off(t, c)) = hi;
       *reinterpret_cast<IO*>(sB1u + NT * 128 + sw128_off(t, c)) = f2h<IO>(w - to_f32(hi));
     }
-    for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
-      const int c = i >> 6, t = i & 63;
-      const float x = (t < p.T && c < C) ? we[c * p.T + t] * p.scale : 0.f;
+    for (int i = threadIdx.x; i < C * NT; i += blockDim.x) {
+      const int c = i / NT, t = i - c * NT;
+      const float x = t < p.T ? we[c * p.T + t] * p.scale : 0.f;
       const __nv_bfloat16 hi = __float2bfloat16_rn(x);
       *reinterpret_cast<__nv_bfloat16*>(sB2 + sw128_off(c, t)) = hi;
       *reinterpret_cast<__nv_bfloat16*>(sB2 + 32 * 128 + sw128_off(c, t)) = __float2bfloat16_rn(x - __bfloat162float(hi));
     }
-    // rows of the transposed [a | ds] operand that no thread writes (t >= T) must be zero
+    // rows of the transposed [a | ds] operand that no thread writes (t >= TL) must be zero
     for (int i = threadIdx.x; i < 2 * 2 * (2 * NT) * 128 / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(sBt)[i] = make_uint4(0, 0, 0, 0);
+    fill_mask_operands<IO>(sOnes, sBias, NT, p.mask + (size_t)b * p.T, p.T);
     fence_proxy_async();
   }
   tc_fence_before();
@@ -432,15 +522,18 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       const uint32_t idesc3 = make_idesc(128, C, 1);               // ds (bf16, TMEM) x W.e (bf16)
       const uint32_t idesc4 = make_idesc(128, 2 * NT, fmt_io);     // [dctx; h] x [a | ds], both K-major over pixels
       const int ks1 = C >> 4;
+      const uint64_t d_ones = make_desc_sw128_mn_lbo(smem_u32(sOnes), 2048u);
+      const uint64_t d_bias = make_desc_sw128(smem_u32(sBias));
       auto gemm1 = [&](int it) {
         const int s = it % kBwdStages, use = it / kBwdStages, u = it & 1;
         mbar_wait(&in_full[s], use & 1);
         tc_fence_after();
         const uint32_t st = smem_u32(sIn + s * stage_bytes);
+        umma_f16(tmem + u * 96, d_ones, d_bias, idesc1, 0u);        // S = 0 / -inf per word
         for (int kk = 0; kk < ks1; ++kk) {
           const uint64_t dh_ = make_desc_sw128_mn_lbo(st + box + kk * 2048, (uint32_t)(2 * box));    // h
           const uint64_t dd_ = make_desc_sw128_mn_lbo(st + kk * 2048, (uint32_t)(2 * box));          // dctx
-          umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s)) + 2 * kk, idesc1, kk ? 1u : 0u);
+          umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s)) + 2 * kk, idesc1, 1u);
           umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s + NT * 128)) + 2 * kk, idesc1, 1u);
           umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u)) + 2 * kk, idesc1, kk ? 1u : 0u);
           umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u + NT * 128)) + 2 * kk, idesc1, 1u);
@@ -474,75 +567,92 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       umma_commit(&acc_done);
     }
   } else {
+    // ===================== epilogue (fragment layout, see the forward kernel) =====================
     const int q = warp & 3;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t lane0 = (uint32_t)(q * 32) << 16;
     const int px = q * 32 + lane;
-    uint64_t valid = 0;
-    for (int t = 0; t < p.T; ++t)
-      if (p.mask[(size_t)b * p.T + t] != 0) valid |= 1ull << t;
     IO* dh = (IO*)p.dh + (size_t)b * C * p.HW;
     const IO* dattn = p.dattn ? (const IO*)p.dattn + (size_t)b * p.T * p.HW : nullptr;
+    const StageAddr sd = stage_addr(smem_u32(sStD), C, q, lane);
+    const size_t row8 = (size_t)8 * p.HW;
+    // stmatrix row address inside one [2NT rows][64 px] box of the [a | ds] operand
+    const uint32_t bt_st = (uint32_t)(q >> 1) * ((2 * NT) * 128) + (lane & 7) * 128 +
+                           (((((q & 1) << 2) + (lane >> 3)) ^ (lane & 7)) << 4);
 
     auto softmax_phase = [&](int it) {
       const int u = it & 1, k = it >> 1;
-      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
       mbar_wait(&s_full[u], k & 1);
       tc_fence_after();
-      float s[TL], g[TL];
-      tmem_ld_cols<TL>(tmem + lane_addr + u * 96, s);
-      tmem_ld_cols<TL>(tmem + lane_addr + u * 96 + NT, g);
+      float s[2][4 * KB], g[2][4 * KB];
+      tmem_ld_frag<KB>(tmem + lane0 + u * 96, s[0]);
+      tmem_ld_frag<KB>(tmem + lane0 + kHalfLanes + u * 96, s[1]);
+      tmem_ld_frag<KB>(tmem + lane0 + u * 96 + NT, g[0]);
+      tmem_ld_frag<KB>(tmem + lane0 + kHalfLanes + u * 96 + NT, g[1]);
       tmem_ld_wait();
-      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      frag_softmax<KB>(s);
+      if (dattn != nullptr) {                        // rare: a gradient arrives through the attention maps too
+        const int pix0 = (blockIdx.x + it * p.ctas_per_sample) * 128 + q * 32 + (lane >> 2);
 #pragma unroll
-      for (int t = 0; t < TL; ++t) {
-        if (!((valid >> t) & 1)) s[t] = -INFINITY;
-        m4[t & 3] = fmaxf(m4[t & 3], s[t]);
-      }
-      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int t = 0; t < TL; ++t) {
-        s[t] = exp2f(s[t] - mx);
-        s4[t & 3] += s[t];
-      }
-      const float inv = 1.f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));
-      float d4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int t = 0; t < TL; ++t) {
-        s[t] *= inv;
-        if (dattn != nullptr && t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)t * p.HW + pix]);
-        if (t >= p.T) g[t] = 0.f;
-        d4[t & 3] = fmaf(s[t], g[t], d4[t & 3]);
-      }
-      const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-      uint32_t pk[NT];                               // [0,16): ds hi pairs, [16,32): ds lo pairs (bf16)
-      unsigned char* btu = sBt + u * (2 * (2 * NT) * 128) + (px >> 6) * ((2 * NT) * 128);
-      const int pc = px & 63;
-      const bool live = pix < p.HW;                  // pixels past the end of the map contribute nothing
-#pragma unroll
-      for (int t = 0; t < NT; t += 2) {
-        if (t < TL) {
-          float d0 = s[t] * (g[t] - dot), d1 = s[t + 1] * (g[t + 1] - dot);
-          if (!live) { d0 = 0.f; d1 = 0.f; }
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
-          const __nv_bfloat16 l0 = __float2bfloat16_rn(d0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(d1 - __bfloat162float(h1));
-          pk[t / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          pk[16 + t / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          if (t < p.T) {
-            *reinterpret_cast<IO*>(btu + sw128_off(t, pc)) = f2h<IO>(live ? s[t] : 0.f);
-            *reinterpret_cast<IO*>(btu + sw128_off(NT + t, pc)) = f2h<IO>(d0);
+          for (int i = 0; i < 4 * KB; ++i) {
+            const int pix = pix0 + 16 * h + 8 * ((i >> 1) & 1);
+            const int t = 8 * (i >> 2) + 2 * (lane & 3) + (i & 1);
+            if (t < p.T && pix < p.HW) g[h][i] += to_f32(dattn[(size_t)t * p.HW + pix]);
           }
-          if (t + 1 < p.T) {
-            *reinterpret_cast<IO*>(btu + sw128_off(t + 1, pc)) = f2h<IO>(live ? s[t + 1] : 0.f);
-            *reinterpret_cast<IO*>(btu + sw128_off(NT + t + 1, pc)) = f2h<IO>(d1);
-          }
-        } else {
-          pk[t / 2] = 0u;
-          pk[16 + t / 2] = 0u;
+      }
+      // ds = a (g - sum_t a g); kept in g
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float dot = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) dot = fmaf(s[h][4 * kk + 2 * j + e], g[h][4 * kk + 2 * j + e], dot);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+          for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) g[h][4 * kk + 2 * j + e] = s[h][4 * kk + 2 * j + e] * (g[h][4 * kk + 2 * j + e] - dot);
         }
+      // ds -> TMEM as bf16 hi + lo (A operand of GEMM3): 32-bit columns [0,16) hi, [16,32) lo
+      constexpr int PB = NT / 8;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t hi[2 * PB], lo[2 * PB];
+#pragma unroll
+        for (int kk = 0; kk < PB; ++kk)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (kk < KB) {
+              const float d0 = g[h][4 * kk + 2 * j], d1 = g[h][4 * kk + 2 * j + 1];
+              const uint32_t ph = pack2<__nv_bfloat16>(d0, d1);
+              hi[2 * kk + j] = ph;
+              lo[2 * kk + j] = pack2<__nv_bfloat16>(d0 - __uint_as_float(ph << 16), d1 - __uint_as_float(ph & 0xffff0000u));
+            } else {
+              hi[2 * kk + j] = 0u;
+              lo[2 * kk + j] = 0u;
+            }
+          }
+        tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * 96, hi);
+        tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * 96 + 16, lo);
       }
-      tmem_st16(tmem + lane_addr + u * 96, pk);
-      tmem_st16(tmem + lane_addr + u * 96 + 16, pk + 16);
+      // [a | ds] transposed into the K-major (over pixels) B operand of GEMM4
+      const uint32_t bt = smem_u32(sBt) + u * (2 * (2 * NT) * 128) + bt_st;
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) {
+        uint32_t ra[4], rd[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          ra[m] = pack2<IO>(s[m >> 1][4 * kk + 2 * (m & 1)], s[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+          rd[m] = pack2<IO>(g[m >> 1][4 * kk + 2 * (m & 1)], g[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+        }
+        stsm_x4_trans(bt + kk * 1024, ra[0], ra[1], ra[2], ra[3]);
+        stsm_x4_trans(bt + NT * 128 + kk * 1024, rd[0], rd[1], rd[2], rd[3]);
+      }
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
@@ -551,21 +661,31 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
     };
     auto dh_phase = [&](int it) {
       const int u = it & 1, k = it >> 1;
-      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + px;
       mbar_wait(&dh_full[u], k & 1);
       tc_fence_after();
       for (int c0 = 0; c0 < C; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + lane_addr + u * 96 + 2 * NT + c0, v);
+        float w[2][8];
+        tmem_ldf2(tmem + lane0 + u * 96 + 2 * NT + c0, w[0]);
+        tmem_ldf2(tmem + lane0 + kHalfLanes + u * 96 + 2 * NT + c0, w[1]);
         tmem_ld_wait();
-        if (pix < p.HW) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dh[(size_t)(c0 + j) * p.HW + pix] = f2h<IO>(v[j]);
+        for (int kk = 0; kk < 2; ++kk) {
+          uint32_t r[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+          stsm_x4_trans(sd.st + (c0 / 8 + kk) * 1024, r[0], r[1], r[2], r[3]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dh_empty[u]);
+      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + sd.pxc;
+      IO* dst = dh + (size_t)sd.row * p.HW + pix;
+      for (int i = 0; i < C / 8; ++i) {
+        if (pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sd.ld + i * 1024);
+        dst += row8;
+      }
+      __syncwarp();
     };
     for (int it = 0; it < ntile; ++it) {
       softmax_phase(it);
@@ -578,8 +698,8 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       mbar_wait(&acc_done, 0);
       tc_fence_after();
       float v[2 * NT];
-      tmem_ld32(tmem + lane_addr + kAccCol, v);
-      tmem_ld32(tmem + lane_addr + kAccCol + 32, v + 32);
+      tmem_ld32(tmem + lane0 + kAccCol, v);
+      tmem_ld32(tmem + lane0 + kAccCol + 32, v + 32);
       tmem_ld_wait();
       if (px < C) {
         for (int t = 0; t < NT; ++t) sAcc[px * NT + t] = v[t];                       // rows of dctx x columns of a
@@ -630,7 +750,8 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
   p.tiles = cdiv(HW, 128);
   p.ctas_per_sample = ctas_per_sample;
   const int NT = kBwdNT;
-  const int smem = kBwdStages * 4 * C * 128 + 4 * NT * 128 + 2 * 32 * 128 + 2 * 2 * (2 * NT) * 128 + 2 * C * NT * 4 + 1024;
+  const int smem = kBwdStages * 4 * C * 128 + 4 * NT * 128 + 2 * 32 * 128 + 2 * 2 * (2 * NT) * 128 + 4096 + NT * 128 +
+                   2 * C * 128 + 1024;
   dim3 grid(ctas_per_sample, B);
   const int slot = prof_begin(PROF_ATTN_BWD, st);
 #define AGB_ATTN_BWD_CASE(TLV)                                                                    \

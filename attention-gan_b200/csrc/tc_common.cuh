@@ -225,6 +225,10 @@ __device__ __forceinline__ void tmem_st_frag(uint32_t taddr, const uint32_t* r) 
   else if constexpr (PB >= 4) { tmem_stf4(taddr, r); if constexpr (PB > 4) tmem_st_frag<PB - 4>(taddr + 16, r + 8); }
   else tmem_stf2(taddr, r);
 }
+// two matrices: threads 0-15 supply the row addresses (matrix i/8, row i%8)
+__device__ __forceinline__ void stsm_x2_trans(uint32_t addr, uint32_t r0, uint32_t r1) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1,%2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -238,6 +242,61 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+// ---- thread = lane TMEM stores (32x32b) and packed fragment loads (16x128b) ----------------------
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// N (multiple of 4, <= 32) consecutive 32-bit columns of this thread's lane
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
+  if constexpr (N >= 16) { tmem_st16(taddr, r); if constexpr (N > 16) tmem_st_n<N - 16>(taddr + 16, r + 16); }
+  else if constexpr (N >= 8) { tmem_st8(taddr, r); if constexpr (N > 8) tmem_st_n<N - 8>(taddr + 8, r + 8); }
+  else tmem_st4(taddr, r);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// tcgen05.ld.16x128b.xN: r[2k + j] = 32-bit column 4k + i%4 of row i/4 + 8j of the 16 lanes at taddr.
+// When the columns hold packed 16-bit pairs (t = 2c, 2c+1) this is the stmatrix fragment of the
+// pixel x word matrix: the transposition of a thread-per-row result goes TMEM -> registers -> smem.
+__device__ __forceinline__ void tmem_ldp1(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ldp2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x2.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ldp4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// KB blocks of 8 words (= 4 packed columns) -> r[2 * KB]
+template <int KB>
+__device__ __forceinline__ void tmem_ld_packed(uint32_t taddr, uint32_t* r) {
+  if constexpr (KB >= 4) { tmem_ldp4(taddr, r); if constexpr (KB > 4) tmem_ld_packed<KB - 4>(taddr + 16, r + 8); }
+  else if constexpr (KB >= 2) { tmem_ldp2(taddr, r); if constexpr (KB > 2) tmem_ld_packed<KB - 2>(taddr + 8, r + 4); }
+  else tmem_ldp1(taddr, r);
+}
+// TL (multiple of 8, <= 64) consecutive fp32 columns of this thread's lane
+template <int TL>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+  if constexpr (TL >= 32) { tmem_ld32(taddr, v); if constexpr (TL > 32) tmem_ld_cols<TL - 32>(taddr + 32, v + 32); }
+  else if constexpr (TL >= 16) { tmem_ld16(taddr, v); if constexpr (TL > 16) tmem_ld_cols<TL - 16>(taddr + 16, v + 16); }
+  else tmem_ld8(taddr, v);
 }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");

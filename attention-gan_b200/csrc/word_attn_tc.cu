@@ -17,6 +17,7 @@
 // TMEM: 2 tile buffers x (NT score/P columns + C context columns) = 128 columns per CTA at
 // T <= 32, C <= 32 (256 otherwise), so up to 4 CTAs share an SM and each keeps two tiles in flight.  Warps: 0 = TMA, 1 = MMA, 2-5 = epilogue.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -33,15 +34,6 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 __device__ __forceinline__ uint64_t make_desc_sw128_mn_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -65,9 +57,14 @@ struct AttnFwdParams {
   int B, C, HW, T;
   float qscale;           // scale * log2(e)
   int tiles, ctas_per_sample;
+  int stages;             // h-tile ring depth of the forward kernel
+  int dbg;                // ablation switches for tuning (AGB_ATTN_DEBUG): 1 = no ctx stores, 2 = no attn stores
 };
 
 constexpr int kAttnStages = 3;
+constexpr int kMaxAttnStages = 8;
+// first tile of CTA x when `tiles` tiles are split into `n` contiguous, balanced ranges
+__device__ __forceinline__ int tile_range_begin(int tiles, int n, int x) { return (int)(((long long)tiles * x) / n); }
 constexpr uint32_t kHalfLanes = 16u << 16;      // TMEM address of the second 16 lanes of a warp's quarter
 
 // Epilogue layout (both kernels).  The epilogue warps read TMEM in the 16x256b fragment layout
@@ -84,7 +81,8 @@ constexpr uint32_t kHalfLanes = 16u << 16;      // TMEM address of the second 16
 
 // per-warp staging geometry inside a [rows x 128 px] tile stored as two swizzled [rows x 64 px] boxes
 struct StageAddr {
-  uint32_t st;      // stmatrix row address of this lane for row block 0 (add 1024 per block of 8 rows)
+  uint32_t st;      // stmatrix.x4 row address of this lane for row block 0 (add 1024 per block of 8 rows)
+  uint32_t st2[2];  // stmatrix.x2 row addresses for the pixel halves h = 0, 1 (matrices j = 0, 1 of that half)
   uint32_t ld;      // ld.shared address of this lane's 16-byte chunk for row block 0
   int row, pxc;     // row (0..7) and pixel offset (multiple of 8, relative to the tile) of that chunk
 };
@@ -93,42 +91,44 @@ __device__ __forceinline__ StageAddr stage_addr(uint32_t base, int rows, int q, 
   const uint32_t box = base + (uint32_t)(q >> 1) * (uint32_t)(rows * 128);
   const int sr = lane & 7, sm = lane >> 3;
   a.st = box + sr * 128 + (((((q & 1) << 2) + sm) ^ sr) << 4);
-  a.row = lane >> 2;
+  a.st2[0] = box + sr * 128 + (((((q & 1) << 2) + (sm & 1)) ^ sr) << 4);
+  a.st2[1] = box + sr * 128 + (((((q & 1) << 2) + 2 + (sm & 1)) ^ sr) << 4);
+  // rows r and r + 4 keep their chunks in opposite halves of the 128-byte line: pairing them inside a
+  // quarter-warp makes the 128-bit reads conflict-free
+  a.row = ((lane >> 2) & 1) * 4 + (lane >> 3);
   const int cq = lane & 3;
   a.ld = box + a.row * 128 + (((((q & 1) << 2) + cq) ^ (a.row & 7)) << 4);
   a.pxc = q * 32 + cq * 8;
   return a;
 }
 
-// softmax over the KB*8 columns of the four pixel rows a thread owns; v[h][4k + 2j + e]
+// softmax over the KB*8 columns of the two pixel rows (j = 0, 1) of one 16-lane half; v[4k + 2j + e]
 template <int KB>
-__device__ __forceinline__ void frag_softmax(float (&v)[2][4 * KB]) {
+__device__ __forceinline__ void frag_softmax(float (&v)[4 * KB]) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int j = 0; j < 2; ++j) {
+    float mx = fmaxf(v[2 * j], v[2 * j + 1]);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      float mx = fmaxf(v[h][2 * j], v[h][2 * j + 1]);
+    for (int k = 1; k < KB; ++k) mx = fmaxf(mx, fmaxf(v[4 * k + 2 * j], v[4 * k + 2 * j + 1]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
 #pragma unroll
-      for (int k = 1; k < KB; ++k) mx = fmaxf(mx, fmaxf(v[h][4 * k + 2 * j], v[h][4 * k + 2 * j + 1]));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      float sum = 0.f;
+    for (int k = 0; k < KB; ++k)
 #pragma unroll
-      for (int k = 0; k < KB; ++k)
+      for (int e = 0; e < 2; ++e) {
+        const float x = exp2f(v[4 * k + 2 * j + e] - mx);   // all masked: (-inf) - (-inf) = NaN, like the reference
+        v[4 * k + 2 * j + e] = x;
+        sum += x;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = __fdividef(1.f, sum);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float x = exp2f(v[h][4 * k + 2 * j + e] - mx);   // all masked: (-inf) - (-inf) = NaN, like the reference
-          v[h][4 * k + 2 * j + e] = x;
-          sum += x;
-        }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float inv = __fdividef(1.f, sum);
+    for (int k = 0; k < KB; ++k)
 #pragma unroll
-      for (int k = 0; k < KB; ++k)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) v[h][4 * k + 2 * j + e] *= inv;
-    }
+      for (int e = 0; e < 2; ++e) v[4 * k + 2 * j + e] *= inv;
+  }
 }
 
 // constant operands of the mask-bias MMA: sOnes = MN-major [16 k][128 px] (two 64-px halves, 2 KB
@@ -149,18 +149,36 @@ __device__ __forceinline__ void fill_mask_operands(unsigned char* sOnes, unsigne
   }
 }
 
-// TL = number of word columns the epilogue touches (T rounded up to 8); NT = MMA N (32 or 64)
-template <typename IO, int NT, int TL>
-__global__ void __launch_bounds__(192)
+// Persistent CTAs.  The B * tiles pixel tiles of the launch are split into gridDim.x contiguous,
+// balanced ranges; a range that crosses a sample boundary is processed as two (or more) segments,
+// each with its own W.e / mask operands.  Warp roles (320 threads): 0 = TMA producer (runs ahead across
+// segments), 1 = MMA issuer, 2-5 = softmax warps (S -> P), 6-9 = output warps (ctx and attention maps
+// -> global).  Warps 1-9 rebuild the operands between segments behind a named barrier.
+// TL = word columns the epilogue touches (T rounded up to 8); NT = MMA N (32 or 64); CT = channels
+constexpr int kFwdThreads = 320;
+template <int NT, int CT> constexpr int fwd_min_ctas() { return (NT == 32 && CT <= 32) ? 3 : (CT <= 32 ? 2 : 1); }
+
+struct Segment { int b, tile0, n; };
+// next segment of the global tile range [g, g1): the tiles of one sample
+__device__ __forceinline__ Segment next_segment(long long g, long long g1, int tiles) {
+  Segment s;
+  s.b = (int)(g / tiles);
+  s.tile0 = (int)(g - (long long)s.b * tiles);
+  s.n = (int)(((long long)(tiles - s.tile0) < g1 - g) ? (long long)(tiles - s.tile0) : g1 - g);
+  return s;
+}
+
+template <typename IO, int NT, int TL, int CT>
+__global__ void __launch_bounds__(kFwdThreads, (fwd_min_ctas<NT, CT>()))
 word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdParams p) {
   constexpr int KB = TL / 8;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-  const int C = p.C;
-  const int box_bytes = C * 128;                 // one [C x 64 px] box
-  const int stage_bytes = 2 * box_bytes;
+  constexpr int C = CT;
+  const int nst = p.stages;                      // depth of the h-tile ring (2..kMaxAttnStages)
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr int box_bytes = C * 128;             // one [C x 64 px] box
+  constexpr int stage_bytes = 2 * box_bytes;
   unsigned char* sH = smem;
-  unsigned char* sB1hi = smem + kAttnStages * stage_bytes;   // [NT rows t][64 k=c]  io type
+  unsigned char* sB1hi = smem + nst * stage_bytes;   // [NT rows t][64 k=c]  io type
   unsigned char* sB1lo = sB1hi + NT * 128;
   unsigned char* sB2hi = sB1lo + NT * 128;                   // [C rows c][64 k=t]   fp16
   unsigned char* sB2lo = sB2hi + box_bytes;
@@ -168,17 +186,23 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
   unsigned char* sBias = sOnes + 4096;                       // [NT rows t][64 k]
   unsigned char* sStA = sBias + NT * 128;                    // attn staging: 2 boxes x [TL rows][64 px]
   unsigned char* sStC = sStA + 2 * TL * 128;                 // ctx staging:  2 boxes x [C rows][64 px]
-  __shared__ uint64_t h_full[kAttnStages], h_empty[kAttnStages], s_full[2], p_ready[2], c_full[2], c_empty[2];
-  __shared__ uint32_t tmem_base_s;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStC + 2 * box_bytes);
+  uint64_t* h_full = bars;                                   // [kMaxAttnStages]
+  uint64_t* h_empty = h_full + kMaxAttnStages;               // [kMaxAttnStages]
+  uint64_t* s_full = h_empty + kMaxAttnStages;               // [2]
+  uint64_t* p_ready = s_full + 2;                            // [2]
+  uint64_t* c_full = p_ready + 2;                            // [2]
+  uint64_t* c_empty = c_full + 2;                            // [2]
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(c_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int bufc = NT + C;                       // TMEM columns of one tile buffer: scores/P + context
-  const uint32_t tmem_cols = 2 * bufc <= 128 ? 128u : 256u;
-  const int ntile = (p.tiles - (int)blockIdx.x + p.ctas_per_sample - 1) / p.ctas_per_sample;   // tiles of this CTA
+  constexpr int bufc = NT + C;                   // TMEM columns of one tile buffer: scores/P + context
+  constexpr uint32_t tmem_cols = 2 * bufc <= 128 ? 128u : 256u;
+  const long long total = (long long)p.B * p.tiles;
+  const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kAttnStages; ++i) {
+    for (int i = 0; i < nst; ++i) {
       mbar_init(&h_full[i], 1);
       mbar_init(&h_empty[i], 1);
     }
@@ -190,197 +214,274 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
-  // B operands of both GEMMs from W.e of this sample: hi + lo 16-bit split, K-major swizzled rows
-  {
-    const float* we = p.we + (size_t)b * C * p.T;
-    for (int i = threadIdx.x; i < NT * C; i += blockDim.x) {        // B1[t][c]
-      const int t = i / C, c = i - t * C;
-      const float x = t < p.T ? we[c * p.T + t] * p.qscale : 0.f;
-      const IO hi = f2h<IO>(x);
-      const IO lo = f2h<IO>(x - to_f32(hi));
-      *reinterpret_cast<IO*>(sB1hi + sw128_off(t, c)) = hi;
-      *reinterpret_cast<IO*>(sB1lo + sw128_off(t, c)) = lo;
-    }
-    for (int i = threadIdx.x; i < C * NT; i += blockDim.x) {        // B2[c][t]
-      const int c = i / NT, t = i - c * NT;
-      const float x = t < p.T ? we[c * p.T + t] : 0.f;
-      const __half hi = __float2half_rn(x);
-      const __half lo = __float2half_rn(x - __half2float(hi));
-      *reinterpret_cast<__half*>(sB2hi + sw128_off(c, t)) = hi;
-      *reinterpret_cast<__half*>(sB2lo + sw128_off(c, t)) = lo;
-    }
-    fill_mask_operands<IO>(sOnes, sBias, NT, p.mask + (size_t)b * p.T, p.T);
-    fence_proxy_async();
+  if (warp == 0) tmem_alloc(tmem_base_s, tmem_cols);
+  // constant operand of the mask-bias MMA; the per-sample bias column is rewritten per segment
+  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) {
+    const uint32_t one2 = pack2<IO>(1.f, 1.f);
+    reinterpret_cast<uint4*>(sOnes)[i] = ((i >> 3) & 15) == 0 ? make_uint4(one2, one2, one2, one2) : make_uint4(0, 0, 0, 0);
   }
+  for (int i = threadIdx.x; i < NT * 128 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sBias)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = *tmem_base_s;
   constexpr int fmt_io = std::is_same<IO, __nv_bfloat16>::value ? 1 : 0;
+  const int q = warp & 3;
+  const uint32_t lane0 = (uint32_t)(q * 32) << 16;
+  const size_t row8 = (size_t)8 * p.HW;
 
   if (warp == 0) {
-    // ===================== TMA producer: h tiles =====================
+    // ===================== TMA producer: h tiles of all segments =====================
     if (elect_one()) {
-      for (int it = 0; it < ntile; ++it) {
-        const int s = it % kAttnStages, use = it / kAttnStages;
-        const int tile = blockIdx.x + it * p.ctas_per_sample;
-        mbar_wait(&h_empty[s], (use & 1) ^ 1);
-        mbar_expect_tx(&h_full[s], (uint32_t)stage_bytes);
-        tma_load_2d(sH + s * stage_bytes, &mapH, &h_full[s], tile * 128, b * C);
-        tma_load_2d(sH + s * stage_bytes + box_bytes, &mapH, &h_full[s], tile * 128 + 64, b * C);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      const uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);   // A MN-major (pixels contiguous)
-      const uint32_t idesc2 = make_idesc(128, C, 0);                       // P (TMEM) x W.e, fp16
-      const int ks1 = C >> 4, ks2 = (TL + 15) >> 4;
-      const uint64_t d_ones = make_desc_sw128_mn_lbo(smem_u32(sOnes), 2048u);
-      const uint64_t d_bias = make_desc_sw128(smem_u32(sBias));
-      auto gemm1 = [&](int it) {
-        const int s = it % kAttnStages, use = it / kAttnStages, u = it & 1;
-        mbar_wait(&h_full[s], use & 1);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sH + s * stage_bytes);
-        umma_f16(tmem + u * bufc, d_ones, d_bias, idesc1, 0u);            // S = 0 / -inf per word
-        for (int kk = 0; kk < ks1; ++kk) {
-          const uint64_t da = make_desc_sw128_mn_lbo(a0 + kk * 2048, (uint32_t)box_bytes);
-          umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1hi)) + 2 * kk, idesc1, 1u);
-          umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1lo)) + 2 * kk, idesc1, 1u);
+      int it = 0;
+      for (long long g = g0; g < g1;) {
+        const Segment sg = next_segment(g, g1, p.tiles);
+        for (int i = 0; i < sg.n; ++i, ++it) {
+          const int s = it % nst, use = it / nst;
+          mbar_wait(&h_empty[s], (use & 1) ^ 1);
+          mbar_expect_tx(&h_full[s], (uint32_t)stage_bytes);
+          tma_load_2d(sH + s * stage_bytes, &mapH, &h_full[s], (sg.tile0 + i) * 128, sg.b * C);
+          tma_load_2d(sH + s * stage_bytes + box_bytes, &mapH, &h_full[s], (sg.tile0 + i) * 128 + 64, sg.b * C);
         }
-        umma_commit(&h_empty[s]);
-        umma_commit(&s_full[u]);
-      };
-      if (ntile > 0) gemm1(0);
-      if (ntile > 1) gemm1(1);
-      for (int it = 0; it < ntile; ++it) {
-        const int u = it & 1, k = it >> 1;
-        mbar_wait(&p_ready[u], k & 1);
-        mbar_wait(&c_empty[u], (k & 1) ^ 1);
-        tc_fence_after();
-        for (int kk = 0; kk < ks2; ++kk) {
-          umma_f16_ts(tmem + u * bufc + NT, tmem + u * bufc + kk * 8, make_desc_sw128(smem_u32(sB2hi)) + 2 * kk, idesc2,
-                      kk ? 1u : 0u);
-          umma_f16_ts(tmem + u * bufc + NT, tmem + u * bufc + kk * 8, make_desc_sw128(smem_u32(sB2lo)) + 2 * kk, idesc2, 1u);
-        }
-        umma_commit(&c_full[u]);
-        if (it + 2 < ntile) gemm1(it + 2);
+        g += sg.n;
       }
     }
   } else {
-    // ===================== epilogue (fragment layout, see above) =====================
-    const int q = warp & 3;
-    const uint32_t lane0 = (uint32_t)(q * 32) << 16;
-    IO* ctx = (IO*)p.ctx + (size_t)b * p.ctx_bs;
-    IO* attn = p.attn ? (IO*)p.attn + (size_t)b * p.T * p.HW : nullptr;
-    const StageAddr sa = stage_addr(smem_u32(sStA), TL, q, lane);
-    const StageAddr sc = stage_addr(smem_u32(sStC), C, q, lane);
-    const size_t row8 = (size_t)8 * p.HW;
-
-    auto softmax_phase = [&](int it) {
-      const int u = it & 1, k = it >> 1;
-      mbar_wait(&s_full[u], k & 1);
-      tc_fence_after();
-      float v[2][4 * KB];
-      tmem_ld_frag<KB>(tmem + lane0 + u * bufc, v[0]);
-      tmem_ld_frag<KB>(tmem + lane0 + kHalfLanes + u * bufc, v[1]);
-      tmem_ld_wait();
-      frag_softmax<KB>(v);
-      constexpr int PB = 2 * ((TL + 15) / 16);   // column blocks of 8 words GEMM2 reads (K = 16 per step)
-      uint32_t pk[2][2 * PB];
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int kk = 0; kk < PB; ++kk)
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            pk[h][2 * kk + j] = kk < KB ? pack2<__half>(v[h][4 * kk + 2 * j], v[h][4 * kk + 2 * j + 1]) : 0u;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * bufc, pk[h]);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[u]);
-      if (attn != nullptr) {
-#pragma unroll
-        for (int kk = 0; kk < KB; ++kk) {
-          uint32_t r[4];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if constexpr (std::is_same<IO, __half>::value) r[m] = pk[m >> 1][2 * kk + (m & 1)];
-            else r[m] = pack2<IO>(v[m >> 1][4 * kk + 2 * (m & 1)], v[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+    const int tid = threadIdx.x - 32;            // 0..287 over warps 1-9
+    int it0 = 0;                                 // tiles of earlier segments (mbarrier phases run on)
+    for (long long g = g0; g < g1;) {
+      const Segment sg = next_segment(g, g1, p.tiles);
+      const int b = sg.b;
+      const int ntile = ((p.dbg & 16) && warp != 1) ? 0 : sg.n;
+      // ---- operands of this sample: W.e hi + lo 16-bit split, K-major swizzled rows; mask bias ----
+      {
+        const float* we = p.we + (size_t)b * C * p.T;
+        for (int i = tid; i < NT * C; i += kFwdThreads - 32) {        // B1[t][c]
+          const int t = i / C, c = i - t * C;
+          const float x = t < p.T ? we[c * p.T + t] * p.qscale : 0.f;
+          const IO hi = f2h<IO>(x);
+          const IO lo = f2h<IO>(x - to_f32(hi));
+          *reinterpret_cast<IO*>(sB1hi + sw128_off(t, c)) = hi;
+          *reinterpret_cast<IO*>(sB1lo + sw128_off(t, c)) = lo;
+        }
+        for (int i = tid; i < C * NT; i += kFwdThreads - 32) {        // B2[c][t]
+          const int c = i / NT, t = i - c * NT;
+          const float x = t < p.T ? we[c * p.T + t] : 0.f;
+          const __half hi = __float2half_rn(x);
+          const __half lo = __float2half_rn(x - __half2float(hi));
+          *reinterpret_cast<__half*>(sB2hi + sw128_off(c, t)) = hi;
+          *reinterpret_cast<__half*>(sB2lo + sw128_off(c, t)) = lo;
+        }
+        for (int t = tid; t < NT; t += kFwdThreads - 32) {
+          const bool keep = t < p.T && p.mask[(size_t)b * p.T + t] != 0;
+          *reinterpret_cast<IO*>(sBias + sw128_off(t, 0)) = f2h<IO>(keep ? 0.f : -INFINITY);
+        }
+        fence_proxy_async();
+        named_bar_sync(1, kFwdThreads - 32);
+      }
+      if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+          constexpr uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);   // A MN-major (pixels contiguous)
+          constexpr uint32_t idesc2 = make_idesc(128, C, 0);                       // P (TMEM) x W.e, fp16
+          constexpr int ks1 = C >> 4, ks2 = (TL + 15) >> 4;
+          const uint64_t d_ones = make_desc_sw128_mn_lbo(smem_u32(sOnes), 2048u);
+          const uint64_t d_bias = make_desc_sw128(smem_u32(sBias));
+          tc_fence_after();
+          // event-driven issue: GEMM1 of tile j1 needs its h tile and the TMEM buffer (output warps done
+          // with tile j1 - 2); GEMM2 of tile j2 needs P from the softmax warps.  Neither blocks the other.
+          int j1 = 0, j2 = 0;
+          if (p.dbg & 16) {                       // tuning: pure TMA streaming rate
+            for (int j = 0; j < ntile; ++j) {
+              mbar_wait(&h_full[(it0 + j) % nst], ((it0 + j) / nst) & 1);
+              mbar_arrive(&h_empty[(it0 + j) % nst]);
+            }
+            j2 = ntile;
           }
-          stsm_x4_trans(sa.st + kk * 1024, r[0], r[1], r[2], r[3]);
+          while (j2 < ntile) {
+            const int i1 = it0 + j1, i2 = it0 + j2;
+            if (j1 < ntile && j1 < j2 + 2 && mbar_try_wait(&h_full[i1 % nst], (i1 / nst) & 1) &&
+                (i1 < 2 || mbar_try_wait(&c_empty[i1 & 1], ((i1 - 2) >> 1) & 1))) {
+              const int s = i1 % nst, u = i1 & 1;
+              tc_fence_after();
+              const uint32_t a0 = smem_u32(sH + s * stage_bytes);
+              umma_f16(tmem + u * bufc, d_ones, d_bias, idesc1, 0u);            // S = 0 / -inf per word
+#pragma unroll
+              for (int kk = 0; kk < ks1; ++kk) {
+                const uint64_t da = make_desc_sw128_mn_lbo(a0 + kk * 2048, (uint32_t)box_bytes);
+                umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1hi)) + 2 * kk, idesc1, 1u);
+                umma_f16(tmem + u * bufc, da, make_desc_sw128(smem_u32(sB1lo)) + 2 * kk, idesc1, 1u);
+              }
+              umma_commit(&h_empty[s]);
+              umma_commit(&s_full[u]);
+              ++j1;
+            }
+            if (j2 < j1 && mbar_try_wait(&p_ready[i2 & 1], (i2 >> 1) & 1)) {
+              const int u = i2 & 1;
+              tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < ks2; ++kk) {
+                umma_f16_ts(tmem + u * bufc + NT, tmem + u * bufc + kk * 8, make_desc_sw128(smem_u32(sB2hi)) + 2 * kk,
+                            idesc2, kk ? 1u : 0u);
+                umma_f16_ts(tmem + u * bufc + NT, tmem + u * bufc + kk * 8, make_desc_sw128(smem_u32(sB2lo)) + 2 * kk,
+                            idesc2, 1u);
+              }
+              umma_commit(&c_full[u]);
+              ++j2;
+            }
+          }
         }
         __syncwarp();
-        const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + sa.pxc;
-        IO* dst = attn + (size_t)sa.row * p.HW + pix;
+      } else if (warp < 6) {
+        // ===================== softmax warps: thread = pixel, no cross-lane traffic =====================
+        // P (fp16 pairs) -> TMEM columns [0, NT/2) of the buffer = A operand of GEMM2.  The attention maps
+        // in the caller's dtype go to columns [NT/2, NT) as packed pairs; the output warps read them back
+        // in the 16x128b fragment layout, which transposes them for stmatrix (fp16 maps: P itself is read).
+        const bool want_attn = p.attn != nullptr;
+        for (int j = 0; j < ntile; ++j) {
+          const int it = it0 + j, u = it & 1, k = it >> 1;
+          mbar_wait(&s_full[u], k & 1);
+          tc_fence_after();
+          if (p.dbg & 4) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[u]);
+            continue;
+          }
+          float v[TL];
+          tmem_ld_cols<TL>(tmem + lane0 + u * bufc, v);
+          tmem_ld_wait();
+          float mx = fmaxf(v[0], v[1]);
 #pragma unroll
-        for (int i = 0; i < KB; ++i) {
-          if (sa.row + 8 * i < p.T && pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sa.ld + i * 1024);
-          dst += row8;
+          for (int t = 2; t < TL; t += 2) mx = fmaxf(mx, fmaxf(v[t], v[t + 1]));
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int t = 0; t < TL; ++t) {
+            v[t] = exp2f(v[t] - mx);             // all masked: (-inf) - (-inf) = NaN, like the reference
+            s4[t & 3] += v[t];
+          }
+          const float inv = __fdividef(1.f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+          uint32_t pk[NT / 2];
+#pragma unroll
+          for (int t = 0; t < NT; t += 2) {
+            if (t < TL) {
+              v[t] *= inv;
+              v[t + 1] *= inv;
+              pk[t / 2] = pack2<__half>(v[t], v[t + 1]);
+            } else {
+              pk[t / 2] = 0u;
+            }
+          }
+          tmem_st_n<NT / 2>(tmem + lane0 + u * bufc, pk);
+          if constexpr (!std::is_same<IO, __half>::value) {
+            if (want_attn) {
+              uint32_t pa[TL / 2];
+#pragma unroll
+              for (int t = 0; t < TL; t += 2) pa[t / 2] = pack2<IO>(v[t], v[t + 1]);
+              tmem_st_n<TL / 2>(tmem + lane0 + u * bufc + NT / 2, pa);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[u]);
         }
-        __syncwarp();
-      }
-    };
-    auto context_phase = [&](int it) {
-      const int u = it & 1, k = it >> 1;
-      mbar_wait(&c_full[u], k & 1);
-      tc_fence_after();
-      for (int c0 = 0; c0 < C; c0 += 16) {
-        float w[2][8];
-        tmem_ldf2(tmem + lane0 + u * bufc + NT + c0, w[0]);
-        tmem_ldf2(tmem + lane0 + kHalfLanes + u * bufc + NT + c0, w[1]);
-        tmem_ld_wait();
+      } else {
+        // ===================== output warps: ctx and attention maps -> global =====================
+        IO* ctx = (IO*)p.ctx + (size_t)b * p.ctx_bs;
+        IO* attn = p.attn ? (IO*)p.attn + (size_t)b * p.T * p.HW : nullptr;
+        const StageAddr sc = stage_addr(smem_u32(sStC), C, q, lane);
+        const StageAddr sa = stage_addr(smem_u32(sStA), TL, q, lane);
+        constexpr int kAttnCol = std::is_same<IO, __half>::value ? 0 : NT / 2;
+        for (int j = 0; j < ntile; ++j) {
+          const int it = it0 + j, u = it & 1, k = it >> 1;
+          mbar_wait(&c_full[u], k & 1);
+          tc_fence_after();
+          if (p.dbg & 8) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&c_empty[u]);
+            continue;
+          }
+          float w[2][4 * (C / 8)];
+          uint32_t pa[2][2 * KB];
+          tmem_ld_frag<C / 8>(tmem + lane0 + u * bufc + NT, w[0]);
+          tmem_ld_frag<C / 8>(tmem + lane0 + kHalfLanes + u * bufc + NT, w[1]);
+          if (attn != nullptr) {
+            tmem_ld_packed<KB>(tmem + lane0 + u * bufc + kAttnCol, pa[0]);
+            tmem_ld_packed<KB>(tmem + lane0 + kHalfLanes + u * bufc + kAttnCol, pa[1]);
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_empty[u]);
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          uint32_t r[4];
+          for (int kk = 0; kk < C / 8; ++kk) {
+            uint32_t r[4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
-          stsm_x4_trans(sc.st + (c0 / 8 + kk) * 1024, r[0], r[1], r[2], r[3]);
+            for (int m = 0; m < 4; ++m)
+              r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+            stsm_x4_trans(sc.st + kk * 1024, r[0], r[1], r[2], r[3]);
+          }
+          if (attn != nullptr) {
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk)
+              stsm_x4_trans(sa.st + kk * 1024, pa[0][2 * kk], pa[0][2 * kk + 1], pa[1][2 * kk], pa[1][2 * kk + 1]);
+          }
+          __syncwarp();
+          {
+            const int pix = (sg.tile0 + j) * 128 + sc.pxc;
+            IO* dst = ctx + (size_t)sc.row * p.HW + pix;
+#pragma unroll
+            for (int i = 0; i < C / 8; ++i) {
+              if (pix < p.HW && !(p.dbg & 1)) *reinterpret_cast<uint4*>(dst) = lds128(sc.ld + i * 1024);
+              dst += row8;
+            }
+          }
+          if (attn != nullptr) {
+            const int pix = (sg.tile0 + j) * 128 + sa.pxc;
+            IO* dst = attn + (size_t)sa.row * p.HW + pix;
+#pragma unroll
+            for (int i = 0; i < KB; ++i) {
+              if (sa.row + 8 * i < p.T && pix < p.HW && !(p.dbg & 2)) *reinterpret_cast<uint4*>(dst) = lds128(sa.ld + i * 1024);
+              dst += row8;
+            }
+          }
+          __syncwarp();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&c_empty[u]);
-      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + sc.pxc;
-      IO* dst = ctx + (size_t)sc.row * p.HW + pix;
-      for (int i = 0; i < C / 8; ++i) {
-        if (pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sc.ld + i * 1024);
-        dst += row8;
-      }
-      __syncwarp();
-    };
-    for (int it = 0; it < ntile; ++it) {
-      softmax_phase(it);
-      if (it > 0) context_phase(it - 1);
+      // the output warps have seen the last GEMM2 of the segment complete: operands may be rewritten
+      named_bar_sync(1, kFwdThreads - 32);
+      it0 += sg.n;
+      g += sg.n;
     }
-    if (ntile > 0) context_phase(ntile - 1);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);
 }
 
-template <typename IO>
-static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaStream_t st) {
-  CUtensorMap mapH;
-  if (int rc = make_tmap_2d(&mapH, images, (uint64_t)p.B * p.C, (uint64_t)p.HW, (uint32_t)p.C,
-                            std::is_same<IO, __nv_bfloat16>::value))
-    return rc;
-  const int NT = p.T <= 32 ? 32 : 64;
-  const int TL = (p.T + 7) / 8 * 8;
-  const int smem = kAttnStages * 2 * p.C * 128 + 2 * NT * 128 + 2 * p.C * 128 + 4096 + NT * 128 + 2 * TL * 128 +
-                   2 * p.C * 128 + 1024;
-  dim3 grid(p.ctas_per_sample, p.B);
-  const int slot = prof_begin(PROF_ATTN_FWD, st);
+template <typename IO, int CT>
+static int launch_attn_fwd_tc_c(const CUtensorMap& mapH, const AttnFwdParams& p_in, int sms, cudaStream_t st) {
+  const int NT = p_in.T <= 32 ? 32 : 64;
+  const int TL = (p_in.T + 7) / 8 * 8;
+  const int fixed = 2 * NT * 128 + 2 * CT * 128 + 4096 + NT * 128 + 2 * TL * 128 + 2 * CT * 128 + 256;
+  const int per_sm = NT == 32 && CT <= 32 ? 3 : (CT <= 32 ? 2 : 1);
+  // deepest h-tile ring that still lets per_sm CTAs share the SM's 227 KB (1 KB reserved per CTA)
+  int stages = ((227 * 1024) / per_sm - 1024 - fixed) / (2 * CT * 128);
+  stages = std::max(2, std::min(kMaxAttnStages, stages));
+  if (const char* e = getenv("AGB_ATTN_FWD_STAGES")) stages = std::max(2, std::min(kMaxAttnStages, atoi(e)));   // tuning knob
+  AttnFwdParams p = p_in;
+  p.stages = stages;
+  const int smem = stages * 2 * CT * 128 + fixed;
+  long long ctas = (long long)sms * per_sm;
+  if (const char* e = getenv("AGB_ATTN_FWD_CTAS")) ctas = std::max(1, atoi(e));   // tuning knob
+  const int grid = (int)std::min<long long>(ctas, (long long)p.B * p.tiles);
 #define AGB_ATTN_FWD_CASE(NTV, TLV)                                                              \
   {                                                                                               \
-    auto kern = word_attn_fwd_tc_kernel<IO, NTV, TLV>;                                            \
+    auto kern = word_attn_fwd_tc_kernel<IO, NTV, TLV, CT>;                                        \
     AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-    kern<<<grid, 192, smem, st>>>(mapH, p);                                                       \
+    kern<<<grid, kFwdThreads, smem, st>>>(mapH, p);                                               \
   }
   switch ((p.T + 7) / 8) {
     case 1: AGB_ATTN_FWD_CASE(32, 8) break;
@@ -393,6 +494,27 @@ static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaSt
     default: AGB_ATTN_FWD_CASE(64, 64) break;
   }
 #undef AGB_ATTN_FWD_CASE
+  return 0;
+}
+
+template <typename IO>
+static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaStream_t st) {
+  CUtensorMap mapH;
+  if (int rc = make_tmap_2d(&mapH, images, (uint64_t)p.B * p.C, (uint64_t)p.HW, (uint32_t)p.C,
+                            std::is_same<IO, __nv_bfloat16>::value))
+    return rc;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int slot = prof_begin(PROF_ATTN_FWD, st);
+  int rc = 0;
+  switch (p.C) {
+    case 16: rc = launch_attn_fwd_tc_c<IO, 16>(mapH, p, sms, st); break;
+    case 32: rc = launch_attn_fwd_tc_c<IO, 32>(mapH, p, sms, st); break;
+    case 48: rc = launch_attn_fwd_tc_c<IO, 48>(mapH, p, sms, st); break;
+    default: rc = launch_attn_fwd_tc_c<IO, 64>(mapH, p, sms, st); break;
+  }
+  if (rc) return rc;
   prof_end(slot, st);
   return check_launch("word_attn_fwd_tc_kernel");
 }
@@ -426,17 +548,21 @@ constexpr int kBwdNT = 32;
 
 constexpr int kBwdStages = 2;
 
-template <typename IO, int TL>
-__global__ void __launch_bounds__(192)
+// Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer, 2-5 / 6-9 = softmax warpgroups for the
+// even / odd tiles of the CTA (tile buffer u = it & 1 belongs to warpgroup u), 10-13 = dh warps.
+constexpr int kBwdThreads = 448;
+
+template <typename IO, int TL, int CT>
+__global__ void __launch_bounds__(kBwdThreads, 2)
 word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapD,
                         const AttnBwdParams p) {
   constexpr int NT = kBwdNT;
   constexpr int KB = TL / 8;
+  constexpr int C = CT;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-  const int C = p.C;
-  const int box = C * 128;                       // one [C x 64 px] box
-  const int stage_bytes = 4 * box;               // dctx_lo | h_lo | dctx_hi | h_hi
+  constexpr int box = C * 128;                   // one [C x 64 px] box
+  constexpr int stage_bytes = 4 * box;           // dctx_lo | h_lo | dctx_hi | h_hi
   unsigned char* sIn = smem;
   unsigned char* sB1s = smem + kBwdStages * stage_bytes;       // [t][c] scaled*log2e   hi, lo (io type)
   unsigned char* sB1u = sB1s + 2 * NT * 128;                   // [t][c] unscaled       hi, lo (io type)
@@ -451,7 +577,8 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int ntile = (p.tiles - (int)blockIdx.x + p.ctas_per_sample - 1) / p.ctas_per_sample;
+  const int tile0 = tile_range_begin(p.tiles, p.ctas_per_sample, blockIdx.x);
+  const int ntile = tile_range_begin(p.tiles, p.ctas_per_sample, blockIdx.x + 1) - tile0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kBwdStages; ++i) {
@@ -501,12 +628,14 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   const uint32_t tmem = tmem_base_s;
   constexpr int fmt_io = std::is_same<IO, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kAccCol = 192;
+  const int q = warp & 3;
+  const uint32_t lane0 = (uint32_t)(q * 32) << 16;
 
   if (warp == 0) {
     if (elect_one()) {
       for (int it = 0; it < ntile; ++it) {
         const int s = it % kBwdStages, use = it / kBwdStages;
-        const int px0 = (blockIdx.x + it * p.ctas_per_sample) * 128;
+        const int px0 = (tile0 + it) * 128;
         mbar_wait(&in_empty[s], (use & 1) ^ 1);
         mbar_expect_tx(&in_full[s], (uint32_t)stage_bytes);
         unsigned char* st = sIn + s * stage_bytes;
@@ -518,10 +647,10 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);
-      const uint32_t idesc3 = make_idesc(128, C, 1);               // ds (bf16, TMEM) x W.e (bf16)
-      const uint32_t idesc4 = make_idesc(128, 2 * NT, fmt_io);     // [dctx; h] x [a | ds], both K-major over pixels
-      const int ks1 = C >> 4;
+      constexpr uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);
+      constexpr uint32_t idesc3 = make_idesc(128, C, 1);               // ds (bf16, TMEM) x W.e (bf16)
+      constexpr uint32_t idesc4 = make_idesc(128, 2 * NT, fmt_io);     // [dctx; h] x [a | ds], both K-major over pixels
+      constexpr int ks1 = C >> 4;
       const uint64_t d_ones = make_desc_sw128_mn_lbo(smem_u32(sOnes), 2048u);
       const uint64_t d_bias = make_desc_sw128(smem_u32(sBias));
       auto gemm1 = [&](int it) {
@@ -530,6 +659,7 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
         tc_fence_after();
         const uint32_t st = smem_u32(sIn + s * stage_bytes);
         umma_f16(tmem + u * 96, d_ones, d_bias, idesc1, 0u);        // S = 0 / -inf per word
+#pragma unroll
         for (int kk = 0; kk < ks1; ++kk) {
           const uint64_t dh_ = make_desc_sw128_mn_lbo(st + box + kk * 2048, (uint32_t)(2 * box));    // h
           const uint64_t dd_ = make_desc_sw128_mn_lbo(st + kk * 2048, (uint32_t)(2 * box));          // dctx
@@ -547,6 +677,7 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
         mbar_wait(&p_ready[u], k & 1);
         mbar_wait(&dh_empty[u], (k & 1) ^ 1);
         tc_fence_after();
+#pragma unroll
         for (int kk = 0; kk < NT / 16; ++kk) {      // dh = ds (hi + lo) x W.e (hi + lo), lo*lo dropped
           const uint32_t a_hi = tmem + u * 96 + kk * 8, a_lo = tmem + u * 96 + 16 + kk * 8;
           const uint64_t b_hi = make_desc_sw128(smem_u32(sB2)) + 2 * kk, b_lo = make_desc_sw128(smem_u32(sB2 + 32 * 128)) + 2 * kk;
@@ -557,7 +688,9 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
         umma_commit(&dh_full[u]);
         const uint32_t st = smem_u32(sIn + s * stage_bytes);
         const uint32_t bt = smem_u32(sBt + u * (2 * (2 * NT) * 128));
+#pragma unroll
         for (int j = 0; j < 2; ++j)                  // two chunks of 64 pixels
+#pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_f16(tmem + kAccCol, make_desc_sw128(st + j * 2 * box) + 2 * kk,
                      make_desc_sw128(bt + j * (2 * NT) * 128) + 2 * kk, idesc4, (it | j | kk) ? 1u : 0u);
@@ -566,69 +699,62 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       }
       umma_commit(&acc_done);
     }
-  } else {
-    // ===================== epilogue (fragment layout, see the forward kernel) =====================
-    const int q = warp & 3;
-    const uint32_t lane0 = (uint32_t)(q * 32) << 16;
-    const int px = q * 32 + lane;
-    IO* dh = (IO*)p.dh + (size_t)b * C * p.HW;
+  } else if (warp < 10) {
+    // ===================== softmax warpgroup u (fragment layout, see the forward kernel) =====================
+    const int u = warp >= 6 ? 1 : 0;
     const IO* dattn = p.dattn ? (const IO*)p.dattn + (size_t)b * p.T * p.HW : nullptr;
-    const StageAddr sd = stage_addr(smem_u32(sStD), C, q, lane);
-    const size_t row8 = (size_t)8 * p.HW;
-    // stmatrix row address inside one [2NT rows][64 px] box of the [a | ds] operand
-    const uint32_t bt_st = (uint32_t)(q >> 1) * ((2 * NT) * 128) + (lane & 7) * 128 +
-                           (((((q & 1) << 2) + (lane >> 3)) ^ (lane & 7)) << 4);
-
-    auto softmax_phase = [&](int it) {
-      const int u = it & 1, k = it >> 1;
+    // stmatrix.x2 row addresses inside the [2NT rows][64 px] boxes of the [a | ds] operand, per pixel half
+    uint32_t bt_st[2];
+    {
+      const uint32_t base = smem_u32(sBt) + u * (2 * (2 * NT) * 128) + (uint32_t)(q >> 1) * ((2 * NT) * 128) + (lane & 7) * 128;
+      const int sm = (lane >> 3) & 1;
+      bt_st[0] = base + (((((q & 1) << 2) + sm) ^ (lane & 7)) << 4);
+      bt_st[1] = base + (((((q & 1) << 2) + 2 + sm) ^ (lane & 7)) << 4);
+    }
+    constexpr int PB = NT / 8;
+    for (int it = u; it < ntile; it += 2) {
+      const int k = it >> 1;
       mbar_wait(&s_full[u], k & 1);
       tc_fence_after();
-      float s[2][4 * KB], g[2][4 * KB];
-      tmem_ld_frag<KB>(tmem + lane0 + u * 96, s[0]);
-      tmem_ld_frag<KB>(tmem + lane0 + kHalfLanes + u * 96, s[1]);
-      tmem_ld_frag<KB>(tmem + lane0 + u * 96 + NT, g[0]);
-      tmem_ld_frag<KB>(tmem + lane0 + kHalfLanes + u * 96 + NT, g[1]);
-      tmem_ld_wait();
-      frag_softmax<KB>(s);
-      if (dattn != nullptr) {                        // rare: a gradient arrives through the attention maps too
-        const int pix0 = (blockIdx.x + it * p.ctas_per_sample) * 128 + q * 32 + (lane >> 2);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
+        float s[4 * KB], g[4 * KB];
+        tmem_ld_frag<KB>(tmem + lane0 + h * kHalfLanes + u * 96, s);
+        tmem_ld_frag<KB>(tmem + lane0 + h * kHalfLanes + u * 96 + NT, g);
+        tmem_ld_wait();
+        frag_softmax<KB>(s);
+        if (dattn != nullptr) {                      // rare: a gradient arrives through the attention maps too
+          const int pix0 = (tile0 + it) * 128 + q * 32 + 16 * h + (lane >> 2);
 #pragma unroll
           for (int i = 0; i < 4 * KB; ++i) {
-            const int pix = pix0 + 16 * h + 8 * ((i >> 1) & 1);
+            const int pix = pix0 + 8 * ((i >> 1) & 1);
             const int t = 8 * (i >> 2) + 2 * (lane & 3) + (i & 1);
-            if (t < p.T && pix < p.HW) g[h][i] += to_f32(dattn[(size_t)t * p.HW + pix]);
+            if (t < p.T && pix < p.HW) g[i] += to_f32(dattn[(size_t)t * p.HW + pix]);
           }
-      }
-      // ds = a (g - sum_t a g); kept in g
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
+        }
+        // ds = a (g - sum_t a g); kept in g
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           float dot = 0.f;
 #pragma unroll
           for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) dot = fmaf(s[h][4 * kk + 2 * j + e], g[h][4 * kk + 2 * j + e], dot);
+            for (int e = 0; e < 2; ++e) dot = fmaf(s[4 * kk + 2 * j + e], g[4 * kk + 2 * j + e], dot);
           dot += __shfl_xor_sync(0xffffffffu, dot, 1);
           dot += __shfl_xor_sync(0xffffffffu, dot, 2);
 #pragma unroll
           for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) g[h][4 * kk + 2 * j + e] = s[h][4 * kk + 2 * j + e] * (g[h][4 * kk + 2 * j + e] - dot);
+            for (int e = 0; e < 2; ++e) g[4 * kk + 2 * j + e] = s[4 * kk + 2 * j + e] * (g[4 * kk + 2 * j + e] - dot);
         }
-      // ds -> TMEM as bf16 hi + lo (A operand of GEMM3): 32-bit columns [0,16) hi, [16,32) lo
-      constexpr int PB = NT / 8;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        // ds -> TMEM as bf16 hi + lo (A operand of GEMM3): 32-bit columns [0,16) hi, [16,32) lo
         uint32_t hi[2 * PB], lo[2 * PB];
 #pragma unroll
         for (int kk = 0; kk < PB; ++kk)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (kk < KB) {
-              const float d0 = g[h][4 * kk + 2 * j], d1 = g[h][4 * kk + 2 * j + 1];
+              const float d0 = g[4 * kk + 2 * j], d1 = g[4 * kk + 2 * j + 1];
               const uint32_t ph = pack2<__nv_bfloat16>(d0, d1);
               hi[2 * kk + j] = ph;
               lo[2 * kk + j] = pack2<__nv_bfloat16>(d0 - __uint_as_float(ph << 16), d1 - __uint_as_float(ph & 0xffff0000u));
@@ -639,59 +765,58 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
           }
         tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * 96, hi);
         tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * 96 + 16, lo);
-      }
-      // [a | ds] transposed into the K-major (over pixels) B operand of GEMM4
-      const uint32_t bt = smem_u32(sBt) + u * (2 * (2 * NT) * 128) + bt_st;
+        // [a | ds] transposed into the K-major (over pixels) B operand of GEMM4
 #pragma unroll
-      for (int kk = 0; kk < KB; ++kk) {
-        uint32_t ra[4], rd[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          ra[m] = pack2<IO>(s[m >> 1][4 * kk + 2 * (m & 1)], s[m >> 1][4 * kk + 2 * (m & 1) + 1]);
-          rd[m] = pack2<IO>(g[m >> 1][4 * kk + 2 * (m & 1)], g[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+        for (int kk = 0; kk < KB; ++kk) {
+          stsm_x2_trans(bt_st[h] + kk * 1024, pack2<IO>(s[4 * kk], s[4 * kk + 1]), pack2<IO>(s[4 * kk + 2], s[4 * kk + 3]));
+          if constexpr (std::is_same<IO, __nv_bfloat16>::value)
+            stsm_x2_trans(bt_st[h] + NT * 128 + kk * 1024, hi[2 * kk], hi[2 * kk + 1]);
+          else
+            stsm_x2_trans(bt_st[h] + NT * 128 + kk * 1024, pack2<IO>(g[4 * kk], g[4 * kk + 1]),
+                          pack2<IO>(g[4 * kk + 2], g[4 * kk + 3]));
         }
-        stsm_x4_trans(bt + kk * 1024, ra[0], ra[1], ra[2], ra[3]);
-        stsm_x4_trans(bt + NT * 128 + kk * 1024, rd[0], rd[1], rd[2], rd[3]);
       }
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[u]);
-    };
-    auto dh_phase = [&](int it) {
+    }
+  } else {
+    // ===================== dh warps =====================
+    const int px = q * 32 + lane;
+    const int tid = (warp - 10) * 32 + lane;
+    IO* dh = (IO*)p.dh + (size_t)b * C * p.HW;
+    const StageAddr sd = stage_addr(smem_u32(sStD), C, q, lane);
+    const size_t row8 = (size_t)8 * p.HW;
+    for (int it = 0; it < ntile; ++it) {
       const int u = it & 1, k = it >> 1;
       mbar_wait(&dh_full[u], k & 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < C; c0 += 16) {
-        float w[2][8];
-        tmem_ldf2(tmem + lane0 + u * 96 + 2 * NT + c0, w[0]);
-        tmem_ldf2(tmem + lane0 + kHalfLanes + u * 96 + 2 * NT + c0, w[1]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          uint32_t r[4];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
-          stsm_x4_trans(sd.st + (c0 / 8 + kk) * 1024, r[0], r[1], r[2], r[3]);
-        }
-      }
+      float w[2][4 * (C / 8)];
+      tmem_ld_frag<C / 8>(tmem + lane0 + u * 96 + 2 * NT, w[0]);
+      tmem_ld_frag<C / 8>(tmem + lane0 + kHalfLanes + u * 96 + 2 * NT, w[1]);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dh_empty[u]);
-      const int pix = (blockIdx.x + it * p.ctas_per_sample) * 128 + sd.pxc;
+#pragma unroll
+      for (int kk = 0; kk < C / 8; ++kk) {
+        uint32_t r[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+        stsm_x4_trans(sd.st + kk * 1024, r[0], r[1], r[2], r[3]);
+      }
+      __syncwarp();
+      const int pix = (tile0 + it) * 128 + sd.pxc;
       IO* dst = dh + (size_t)sd.row * p.HW + pix;
+#pragma unroll
       for (int i = 0; i < C / 8; ++i) {
         if (pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sd.ld + i * 1024);
         dst += row8;
       }
       __syncwarp();
-    };
-    for (int it = 0; it < ntile; ++it) {
-      softmax_phase(it);
-      if (it > 0) dh_phase(it - 1);
     }
-    if (ntile > 0) dh_phase(ntile - 1);
     // ---- d(W.e) partial of this CTA ----
     float* part = p.part + ((size_t)b * p.ctas_per_sample + blockIdx.x) * C * p.T;
     if (ntile > 0) {
@@ -707,12 +832,12 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
         for (int t = 0; t < NT; ++t) sAcc[C * NT + (px - C) * NT + t] = v[NT + t];   // rows of h x columns of ds
       }
       named_bar_sync(1, 128);
-      for (int i = threadIdx.x - 64; i < C * p.T; i += 128) {
+      for (int i = tid; i < C * p.T; i += 128) {
         const int c = i / p.T, t = i - c * p.T;
         part[i] = sAcc[c * NT + t] + p.scale * sAcc[C * NT + c * NT + t];
       }
     } else {
-      for (int i = threadIdx.x - 64; i < C * p.T; i += 128) part[i] = 0.f;
+      for (int i = tid; i < C * p.T; i += 128) part[i] = 0.f;
     }
   }
   tc_fence_before();
@@ -734,6 +859,7 @@ int word_attn_bwd_tc_ctas(int B, int HW) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = cdiv(HW, 128);
+  if (const char* e = getenv("AGB_ATTN_BWD_CPS")) return std::max(1, std::min(tiles, atoi(e)));   // tuning knob
   return std::max(1, std::min(cdiv(tiles, 2), std::max(1, (sms * 2) / B)));
 }
 
@@ -754,15 +880,21 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
                    2 * C * 128 + 1024;
   dim3 grid(ctas_per_sample, B);
   const int slot = prof_begin(PROF_ATTN_BWD, st);
-#define AGB_ATTN_BWD_CASE(TLV)                                                                    \
+#define AGB_ATTN_BWD_CASE2(TLV, CTV)                                                              \
   if (bf) {                                                                                       \
-    auto kern = word_attn_bwd_tc_kernel<__nv_bfloat16, TLV>;                                      \
+    auto kern = word_attn_bwd_tc_kernel<__nv_bfloat16, TLV, CTV>;                                 \
     AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);                                                 \
+    kern<<<grid, kBwdThreads, smem, st>>>(mapH, mapD, p);                                         \
   } else {                                                                                        \
-    auto kern = word_attn_bwd_tc_kernel<__half, TLV>;                                             \
+    auto kern = word_attn_bwd_tc_kernel<__half, TLV, CTV>;                                        \
     AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-    kern<<<grid, 192, smem, st>>>(mapH, mapD, p);                                                 \
+    kern<<<grid, kBwdThreads, smem, st>>>(mapH, mapD, p);                                         \
+  }
+#define AGB_ATTN_BWD_CASE(TLV)        \
+  if (C == 16) {                      \
+    AGB_ATTN_BWD_CASE2(TLV, 16)       \
+  } else {                            \
+    AGB_ATTN_BWD_CASE2(TLV, 32)       \
   }
   switch ((T + 7) / 8) {
     case 1: AGB_ATTN_BWD_CASE(8) break;
@@ -770,6 +902,7 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
     case 3: AGB_ATTN_BWD_CASE(24) break;
     default: AGB_ATTN_BWD_CASE(32) break;
   }
+#undef AGB_ATTN_BWD_CASE2
 #undef AGB_ATTN_BWD_CASE
   prof_end(slot, st);
   return check_launch("word_attn_bwd_tc_kernel");
@@ -789,14 +922,9 @@ int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, v
   p.we = we; p.mask = mask; p.ctx = ctx; p.attn = attn; p.ctx_bs = ctx_bs;
   p.B = B; p.C = C; p.HW = HW; p.T = T; p.qscale = qscale;
   p.tiles = cdiv(HW, 128);
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  // whole waves of resident CTAs (3 per SM by registers / shared memory), at least 2 tiles each
-  p.ctas_per_sample = std::max(1, std::min(cdiv(p.tiles, 2), std::max(1, (sms * 3) / B)));
+  p.ctas_per_sample = 0;   // the forward kernel is persistent over all samples
+  p.dbg = 0;
+  if (const char* e = getenv("AGB_ATTN_DEBUG")) p.dbg = atoi(e);
   if (io_dtype == AGB_BF16) return launch_attn_fwd_tc<__nv_bfloat16>(images, p, st);
   return launch_attn_fwd_tc<__half>(images, p, st);
 }

@@ -212,6 +212,15 @@ def run_native(args):
     lib = pkg.native.lib()
     peaks = load_peaks()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
+    flush_mode = os.environ.get("AGB_BENCH_FLUSH", "write")
+
+    def l2_flush():
+        # write a buffer larger than L2 (evicts every input line)
+        flush.zero_()
+        if flush_mode == "write_read":
+            # diagnostic: then stream a clean buffer through L2 so no dirty lines remain
+            flush_rd.sum()
 
     def barrier():
         if world > 1:
@@ -359,7 +368,7 @@ def run_native(args):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         for a, b in ev:
-            flush.zero_()                         # L2 flush between timed iterations (outside the events)
+            l2_flush()                            # L2 flush between timed iterations (outside the events)
             a.record()
             run()
             b.record()
@@ -379,7 +388,7 @@ def run_native(args):
     lib.agb_prof_enable(1)
     n0 = lib.agb_launch_count()
     for _ in range(prof_steps):
-        flush.zero_()
+        l2_flush()
         step_dev(ts)
     barrier()
     launches_per_step = (lib.agb_launch_count() - n0) // prof_steps

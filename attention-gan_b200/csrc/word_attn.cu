@@ -22,7 +22,7 @@ int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dct
                                int T, int io_dtype);
 int word_attn_bwd_tc_ctas(int B, int HW);
 int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
-                     void* dimages, float* part, int ctas_per_sample, int B, int C, int HW, int T, int io_dtype,
+                     void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
                      float scale, cudaStream_t st);
 }  // namespace tc
 
@@ -575,19 +575,23 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
   if (use_tc) ntiles = tc::word_attn_bwd_tc_ctas(B, HW);
   float* dwe = part + (size_t)B * ntiles * C * T;
   if (use_tc) {
-    rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dattn, dimages, part, ntiles, B, C, HW, T, io_dtype, scale, st);
-  } else
-  AGB_DISPATCH_TMAX(tm, {
-    constexpr int VV = TMAX <= 24 ? 2 : 1;
-    if (io_dtype == AGB_F32) rc = launch_bwd<float, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
-    else if (io_dtype == AGB_BF16) rc = launch_bwd<__nv_bfloat16, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
-    else rc = launch_bwd<__half, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
-  });
-  if (rc) return rc;
-  // dwe[b] = sum of the partials; dwords[b][e,t] = sum_c W[c,e] dwe[b][c,t]; dW[c,e] = sum_b,t dwe[b][c,t] words[b][e,t]
-  sum_partials_kernel<<<dim3(cdiv(C * T, 128), B), 128, 0, st>>>(part, ntiles, (int64_t)C * T, (int64_t)ntiles * C * T,
-                                                                 C * T, dwe);
-  if ((rc = check_launch("sum_partials_kernel"))) return rc;
+    // tensor-core kernel + its own reduction of the per-CTA partials into dwe
+    rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dattn, dimages, part, ntiles, dwe, B, C, HW, T, io_dtype, scale, st);
+    if (rc) return rc;
+  } else {
+    AGB_DISPATCH_TMAX(tm, {
+      constexpr int VV = TMAX <= 24 ? 2 : 1;
+      if (io_dtype == AGB_F32) rc = launch_bwd<float, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
+      else if (io_dtype == AGB_BF16) rc = launch_bwd<__nv_bfloat16, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
+      else rc = launch_bwd<__half, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
+    });
+    if (rc) return rc;
+    // dwe[b] = sum of the partials
+    sum_partials_kernel<<<dim3(cdiv(C * T, 128), B), 128, 0, st>>>(part, ntiles, (int64_t)C * T, (int64_t)ntiles * C * T,
+                                                                   C * T, dwe);
+    if ((rc = check_launch("sum_partials_kernel"))) return rc;
+  }
+  // dwords[b][e,t] = sum_c W[c,e] dwe[b][c,t]; dW[c,e] = sum_b,t dwe[b][c,t] words[b][e,t]
   if (dwords) {
     SgemmArgs g{};
     g.A = conv_w; g.a_m = 1; g.a_k = E; g.a_batch = 0;

@@ -538,7 +538,8 @@ struct AttnBwdParams {
   const int64_t* mask;
   const void* dattn;      // [B, T, HW] io dtype or null
   void* dh;               // [B, C, HW]
-  float* part;            // [B, ctas_per_sample, C, T] per-CTA partial d(W.e)
+  float* part;            // [B, part_slots, C, T] per-CTA partial d(W.e)
+  int part_slots, stages;
   int B, C, HW, T;
   float scale;
   int tiles, ctas_per_sample;
@@ -546,11 +547,17 @@ struct AttnBwdParams {
 
 constexpr int kBwdNT = 32;
 
-constexpr int kBwdStages = 2;
 
-// Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer, 2-5 / 6-9 = softmax warpgroups for the
-// even / odd tiles of the CTA (tile buffer u = it & 1 belongs to warpgroup u), 10-13 = dh warps.
+// Persistent CTAs over contiguous, balanced ranges of the B * tiles pixel tiles (segments per sample,
+// see the forward kernel).  Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer, 2-5 / 6-9 =
+// softmax warpgroups for the even / odd tiles (tile buffer u = it & 1 belongs to warpgroup u), 10-13 =
+// dh warps.  Softmax threads own one pixel: S and G rows come from TMEM with 32x32b loads, the softmax
+// and its backward need no cross-lane traffic, and the 16-bit results go back to TMEM as packed pairs:
+//   cols [0,16) ds hi, [16,32) ds lo (bf16; A operand of GEMM3), [32,48) a, [48,64) ds in fp16 (fp16 maps)
+// The same warp reads a / ds back in the 16x128b fragment layout and stmatrix.trans-es them into the
+// K-major (over pixels) B operand of GEMM4 -- the transposition costs ~12 instructions per warp.
 constexpr int kBwdThreads = 448;
+constexpr int kMaxBwdStages = 4;
 
 template <typename IO, int TL, int CT>
 __global__ void __launch_bounds__(kBwdThreads, 2)
@@ -559,29 +566,35 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   constexpr int NT = kBwdNT;
   constexpr int KB = TL / 8;
   constexpr int C = CT;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  const int nst = p.stages;
+  extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int box = C * 128;                   // one [C x 64 px] box
   constexpr int stage_bytes = 4 * box;           // dctx_lo | h_lo | dctx_hi | h_hi
+  constexpr int bt_box = 2 * TL * 128;           // one [a rows | ds rows][64 px] box of the GEMM4 B operand
   unsigned char* sIn = smem;
-  unsigned char* sB1s = smem + kBwdStages * stage_bytes;       // [t][c] scaled*log2e   hi, lo (io type)
+  unsigned char* sB1s = smem + nst * stage_bytes;              // [t][c] scaled*log2e   hi, lo (io type)
   unsigned char* sB1u = sB1s + 2 * NT * 128;                   // [t][c] unscaled       hi, lo (io type)
   unsigned char* sB2 = sB1u + 2 * NT * 128;                    // [c][t] * scale        hi, lo (bf16), 32 rows each
-  unsigned char* sBt = sB2 + 2 * 32 * 128;                     // 2 buffers x 2 px-chunks x [2NT rows][64 px]
-  unsigned char* sOnes = sBt + 2 * 2 * (2 * NT) * 128;         // mask-bias MMA operands (see the forward kernel)
+  unsigned char* sBt = sB2 + 2 * 32 * 128;                     // 2 buffers x 2 px-chunks x [2TL rows][64 px]
+  unsigned char* sOnes = sBt + 2 * 2 * bt_box;                 // mask-bias MMA operands (see the forward kernel)
   unsigned char* sBias = sOnes + 4096;
   unsigned char* sStD = sBias + NT * 128;                      // dh staging: 2 boxes x [C rows][64 px]
-  float* sAcc = reinterpret_cast<float*>(sIn);                 // [2][C][NT], aliases the input ring after the last MMA
-  __shared__ uint64_t in_full[kBwdStages], in_empty[kBwdStages], s_full[2], p_ready[2], dh_full[2], dh_empty[2], acc_done;
-  __shared__ uint32_t tmem_base_s;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStD + 2 * box);
+  uint64_t* in_full = bars;                                    // [kMaxBwdStages]
+  uint64_t* in_empty = in_full + kMaxBwdStages;                // [kMaxBwdStages]
+  uint64_t* s_full = in_empty + kMaxBwdStages;                 // [2]
+  uint64_t* p_ready = s_full + 2;                              // [2]
+  uint64_t* dh_full = p_ready + 2;                             // [2]
+  uint64_t* dh_empty = dh_full + 2;                            // [2]
+  uint64_t* acc_done = dh_empty + 2;                           // [1]
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int tile0 = tile_range_begin(p.tiles, p.ctas_per_sample, blockIdx.x);
-  const int ntile = tile_range_begin(p.tiles, p.ctas_per_sample, blockIdx.x + 1) - tile0;
+  const long long total = (long long)p.B * p.tiles;
+  const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kBwdStages; ++i) {
+    for (int i = 0; i < kMaxBwdStages; ++i) {
       mbar_init(&in_full[i], 1);
       mbar_init(&in_empty[i], 1);
     }
@@ -591,253 +604,281 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
       mbar_init(&dh_full[i], 1);
       mbar_init(&dh_empty[i], 4);
     }
-    mbar_init(&acc_done, 1);
+    mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-  {
-    const float* we = p.we + (size_t)b * C * p.T;
-    const float qs = p.scale * kLog2e;
-    for (int i = threadIdx.x; i < NT * C; i += blockDim.x) {
-      const int t = i / C, c = i - t * C;
-      const float w = t < p.T ? we[c * p.T + t] : 0.f;
-      const float xs = w * qs;
-      IO hi = f2h<IO>(xs);
-      *reinterpret_cast<IO*>(sB1s + sw128_off(t, c)) = hi;
-      *reinterpret_cast<IO*>(sB1s + NT * 128 + sw128_off(t, c)) = f2h<IO>(xs - to_f32(hi));
-      hi = f2h<IO>(w);
-      *reinterpret_cast<IO*>(sB1u + sw128_off(t, c)) = hi;
-      *reinterpret_cast<IO*>(sB1u + NT * 128 + sw128_off(t, c)) = f2h<IO>(w - to_f32(hi));
-    }
-    for (int i = threadIdx.x; i < C * NT; i += blockDim.x) {
-      const int c = i / NT, t = i - c * NT;
-      const float x = t < p.T ? we[c * p.T + t] * p.scale : 0.f;
-      const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-      *reinterpret_cast<__nv_bfloat16*>(sB2 + sw128_off(c, t)) = hi;
-      *reinterpret_cast<__nv_bfloat16*>(sB2 + 32 * 128 + sw128_off(c, t)) = __float2bfloat16_rn(x - __bfloat162float(hi));
-    }
-    // rows of the transposed [a | ds] operand that no thread writes (t >= TL) must be zero
-    for (int i = threadIdx.x; i < 2 * 2 * (2 * NT) * 128 / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(sBt)[i] = make_uint4(0, 0, 0, 0);
-    fill_mask_operands<IO>(sOnes, sBias, NT, p.mask + (size_t)b * p.T, p.T);
-    fence_proxy_async();
+  if (warp == 0) tmem_alloc(tmem_base_s, 256);
+  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) {
+    const uint32_t one2 = pack2<IO>(1.f, 1.f);
+    reinterpret_cast<uint4*>(sOnes)[i] = ((i >> 3) & 15) == 0 ? make_uint4(one2, one2, one2, one2) : make_uint4(0, 0, 0, 0);
   }
+  for (int i = threadIdx.x; i < NT * 128 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sBias)[i] = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = *tmem_base_s;
   constexpr int fmt_io = std::is_same<IO, __nv_bfloat16>::value ? 1 : 0;
   constexpr uint32_t kAccCol = 192;
   const int q = warp & 3;
   const uint32_t lane0 = (uint32_t)(q * 32) << 16;
 
   if (warp == 0) {
+    // ===================== TMA producer: dctx and h tiles of all segments =====================
     if (elect_one()) {
-      for (int it = 0; it < ntile; ++it) {
-        const int s = it % kBwdStages, use = it / kBwdStages;
-        const int px0 = (tile0 + it) * 128;
-        mbar_wait(&in_empty[s], (use & 1) ^ 1);
-        mbar_expect_tx(&in_full[s], (uint32_t)stage_bytes);
-        unsigned char* st = sIn + s * stage_bytes;
-        tma_load_2d(st, &mapD, &in_full[s], px0, b * C);
-        tma_load_2d(st + box, &mapH, &in_full[s], px0, b * C);
-        tma_load_2d(st + 2 * box, &mapD, &in_full[s], px0 + 64, b * C);
-        tma_load_2d(st + 3 * box, &mapH, &in_full[s], px0 + 64, b * C);
+      int it = 0;
+      for (long long g = g0; g < g1;) {
+        const Segment sg = next_segment(g, g1, p.tiles);
+        for (int i = 0; i < sg.n; ++i, ++it) {
+          const int s = it % nst, use = it / nst;
+          const int px0 = (sg.tile0 + i) * 128;
+          mbar_wait(&in_empty[s], (use & 1) ^ 1);
+          mbar_expect_tx(&in_full[s], (uint32_t)stage_bytes);
+          unsigned char* st = sIn + s * stage_bytes;
+          tma_load_2d(st, &mapD, &in_full[s], px0, sg.b * C);
+          tma_load_2d(st + box, &mapH, &in_full[s], px0, sg.b * C);
+          tma_load_2d(st + 2 * box, &mapD, &in_full[s], px0 + 64, sg.b * C);
+          tma_load_2d(st + 3 * box, &mapH, &in_full[s], px0 + 64, sg.b * C);
+        }
+        g += sg.n;
       }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);
-      constexpr uint32_t idesc3 = make_idesc(128, C, 1);               // ds (bf16, TMEM) x W.e (bf16)
-      constexpr uint32_t idesc4 = make_idesc(128, 2 * NT, fmt_io);     // [dctx; h] x [a | ds], both K-major over pixels
-      constexpr int ks1 = C >> 4;
-      const uint64_t d_ones = make_desc_sw128_mn_lbo(smem_u32(sOnes), 2048u);
-      const uint64_t d_bias = make_desc_sw128(smem_u32(sBias));
-      auto gemm1 = [&](int it) {
-        const int s = it % kBwdStages, use = it / kBwdStages, u = it & 1;
-        mbar_wait(&in_full[s], use & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(sIn + s * stage_bytes);
-        umma_f16(tmem + u * 96, d_ones, d_bias, idesc1, 0u);        // S = 0 / -inf per word
-#pragma unroll
-        for (int kk = 0; kk < ks1; ++kk) {
-          const uint64_t dh_ = make_desc_sw128_mn_lbo(st + box + kk * 2048, (uint32_t)(2 * box));    // h
-          const uint64_t dd_ = make_desc_sw128_mn_lbo(st + kk * 2048, (uint32_t)(2 * box));          // dctx
-          umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s)) + 2 * kk, idesc1, 1u);
-          umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s + NT * 128)) + 2 * kk, idesc1, 1u);
-          umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u)) + 2 * kk, idesc1, kk ? 1u : 0u);
-          umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u + NT * 128)) + 2 * kk, idesc1, 1u);
-        }
-        umma_commit(&s_full[u]);
-      };
-      if (ntile > 0) gemm1(0);
-      if (ntile > 1) gemm1(1);
-      for (int it = 0; it < ntile; ++it) {
-        const int u = it & 1, k = it >> 1, s = it % kBwdStages;
-        mbar_wait(&p_ready[u], k & 1);
-        mbar_wait(&dh_empty[u], (k & 1) ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < NT / 16; ++kk) {      // dh = ds (hi + lo) x W.e (hi + lo), lo*lo dropped
-          const uint32_t a_hi = tmem + u * 96 + kk * 8, a_lo = tmem + u * 96 + 16 + kk * 8;
-          const uint64_t b_hi = make_desc_sw128(smem_u32(sB2)) + 2 * kk, b_lo = make_desc_sw128(smem_u32(sB2 + 32 * 128)) + 2 * kk;
-          umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_hi, idesc3, kk ? 1u : 0u);
-          umma_f16_ts(tmem + u * 96 + 2 * NT, a_lo, b_hi, idesc3, 1u);
-          umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_lo, idesc3, 1u);
-        }
-        umma_commit(&dh_full[u]);
-        const uint32_t st = smem_u32(sIn + s * stage_bytes);
-        const uint32_t bt = smem_u32(sBt + u * (2 * (2 * NT) * 128));
-#pragma unroll
-        for (int j = 0; j < 2; ++j)                  // two chunks of 64 pixels
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem + kAccCol, make_desc_sw128(st + j * 2 * box) + 2 * kk,
-                     make_desc_sw128(bt + j * (2 * NT) * 128) + 2 * kk, idesc4, (it | j | kk) ? 1u : 0u);
-        umma_commit(&in_empty[s]);
-        if (it + 2 < ntile) gemm1(it + 2);
-      }
-      umma_commit(&acc_done);
-    }
-  } else if (warp < 10) {
-    // ===================== softmax warpgroup u (fragment layout, see the forward kernel) =====================
-    const int u = warp >= 6 ? 1 : 0;
-    const IO* dattn = p.dattn ? (const IO*)p.dattn + (size_t)b * p.T * p.HW : nullptr;
-    // stmatrix.x2 row addresses inside the [2NT rows][64 px] boxes of the [a | ds] operand, per pixel half
-    uint32_t bt_st[2];
-    {
-      const uint32_t base = smem_u32(sBt) + u * (2 * (2 * NT) * 128) + (uint32_t)(q >> 1) * ((2 * NT) * 128) + (lane & 7) * 128;
-      const int sm = (lane >> 3) & 1;
-      bt_st[0] = base + (((((q & 1) << 2) + sm) ^ (lane & 7)) << 4);
-      bt_st[1] = base + (((((q & 1) << 2) + 2 + sm) ^ (lane & 7)) << 4);
-    }
-    constexpr int PB = NT / 8;
-    for (int it = u; it < ntile; it += 2) {
-      const int k = it >> 1;
-      mbar_wait(&s_full[u], k & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float s[4 * KB], g[4 * KB];
-        tmem_ld_frag<KB>(tmem + lane0 + h * kHalfLanes + u * 96, s);
-        tmem_ld_frag<KB>(tmem + lane0 + h * kHalfLanes + u * 96 + NT, g);
-        tmem_ld_wait();
-        frag_softmax<KB>(s);
-        if (dattn != nullptr) {                      // rare: a gradient arrives through the attention maps too
-          const int pix0 = (tile0 + it) * 128 + q * 32 + 16 * h + (lane >> 2);
-#pragma unroll
-          for (int i = 0; i < 4 * KB; ++i) {
-            const int pix = pix0 + 8 * ((i >> 1) & 1);
-            const int t = 8 * (i >> 2) + 2 * (lane & 3) + (i & 1);
-            if (t < p.T && pix < p.HW) g[i] += to_f32(dattn[(size_t)t * p.HW + pix]);
-          }
-        }
-        // ds = a (g - sum_t a g); kept in g
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float dot = 0.f;
-#pragma unroll
-          for (int kk = 0; kk < KB; ++kk)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) dot = fmaf(s[4 * kk + 2 * j + e], g[4 * kk + 2 * j + e], dot);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-#pragma unroll
-          for (int kk = 0; kk < KB; ++kk)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) g[4 * kk + 2 * j + e] = s[4 * kk + 2 * j + e] * (g[4 * kk + 2 * j + e] - dot);
-        }
-        // ds -> TMEM as bf16 hi + lo (A operand of GEMM3): 32-bit columns [0,16) hi, [16,32) lo
-        uint32_t hi[2 * PB], lo[2 * PB];
-#pragma unroll
-        for (int kk = 0; kk < PB; ++kk)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (kk < KB) {
-              const float d0 = g[4 * kk + 2 * j], d1 = g[4 * kk + 2 * j + 1];
-              const uint32_t ph = pack2<__nv_bfloat16>(d0, d1);
-              hi[2 * kk + j] = ph;
-              lo[2 * kk + j] = pack2<__nv_bfloat16>(d0 - __uint_as_float(ph << 16), d1 - __uint_as_float(ph & 0xffff0000u));
-            } else {
-              hi[2 * kk + j] = 0u;
-              lo[2 * kk + j] = 0u;
-            }
-          }
-        tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * 96, hi);
-        tmem_st_frag<PB>(tmem + lane0 + h * kHalfLanes + u * 96 + 16, lo);
-        // [a | ds] transposed into the K-major (over pixels) B operand of GEMM4
-#pragma unroll
-        for (int kk = 0; kk < KB; ++kk) {
-          stsm_x2_trans(bt_st[h] + kk * 1024, pack2<IO>(s[4 * kk], s[4 * kk + 1]), pack2<IO>(s[4 * kk + 2], s[4 * kk + 3]));
-          if constexpr (std::is_same<IO, __nv_bfloat16>::value)
-            stsm_x2_trans(bt_st[h] + NT * 128 + kk * 1024, hi[2 * kk], hi[2 * kk + 1]);
-          else
-            stsm_x2_trans(bt_st[h] + NT * 128 + kk * 1024, pack2<IO>(g[4 * kk], g[4 * kk + 1]),
-                          pack2<IO>(g[4 * kk + 2], g[4 * kk + 3]));
-        }
-      }
-      tmem_st_wait();
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[u]);
     }
   } else {
-    // ===================== dh warps =====================
-    const int px = q * 32 + lane;
-    const int tid = (warp - 10) * 32 + lane;
-    IO* dh = (IO*)p.dh + (size_t)b * C * p.HW;
-    const StageAddr sd = stage_addr(smem_u32(sStD), C, q, lane);
-    const size_t row8 = (size_t)8 * p.HW;
-    for (int it = 0; it < ntile; ++it) {
-      const int u = it & 1, k = it >> 1;
-      mbar_wait(&dh_full[u], k & 1);
-      tc_fence_after();
-      float w[2][4 * (C / 8)];
-      tmem_ld_frag<C / 8>(tmem + lane0 + u * 96 + 2 * NT, w[0]);
-      tmem_ld_frag<C / 8>(tmem + lane0 + kHalfLanes + u * 96 + 2 * NT, w[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dh_empty[u]);
+    constexpr int kWorkers = kBwdThreads - 32;
+    const int tid = threadIdx.x - 32;
+    int it0 = 0, seg = 0;
+    for (long long g = g0; g < g1; ++seg) {
+      const Segment sg = next_segment(g, g1, p.tiles);
+      const int b = sg.b, ntile = sg.n;
+      {
+        const float* we = p.we + (size_t)b * C * p.T;
+        const float qs = p.scale * kLog2e;
+        for (int i = tid; i < NT * C; i += kWorkers) {
+          const int t = i / C, c = i - t * C;
+          const float w = t < p.T ? we[c * p.T + t] : 0.f;
+          const float xs = w * qs;
+          IO hi = f2h<IO>(xs);
+          *reinterpret_cast<IO*>(sB1s + sw128_off(t, c)) = hi;
+          *reinterpret_cast<IO*>(sB1s + NT * 128 + sw128_off(t, c)) = f2h<IO>(xs - to_f32(hi));
+          hi = f2h<IO>(w);
+          *reinterpret_cast<IO*>(sB1u + sw128_off(t, c)) = hi;
+          *reinterpret_cast<IO*>(sB1u + NT * 128 + sw128_off(t, c)) = f2h<IO>(w - to_f32(hi));
+        }
+        for (int i = tid; i < C * NT; i += kWorkers) {
+          const int c = i / NT, t = i - c * NT;
+          const float x = t < p.T ? we[c * p.T + t] * p.scale : 0.f;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+          *reinterpret_cast<__nv_bfloat16*>(sB2 + sw128_off(c, t)) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(sB2 + 32 * 128 + sw128_off(c, t)) = __float2bfloat16_rn(x - __bfloat162float(hi));
+        }
+        for (int t = tid; t < NT; t += kWorkers) {
+          const bool keep = t < p.T && p.mask[(size_t)b * p.T + t] != 0;
+          *reinterpret_cast<IO*>(sBias + sw128_off(t, 0)) = f2h<IO>(keep ? 0.f : -INFINITY);
+        }
+        fence_proxy_async();
+        named_bar_sync(1, kWorkers);
+      }
+      if (warp == 1) {
+        // ===================== MMA issuer (event driven, see the forward kernel) =====================
+        if (elect_one()) {
+          constexpr uint32_t idesc1 = make_idesc(128, NT, fmt_io) | (1u << 15);
+          constexpr uint32_t idesc3 = make_idesc(128, C, 1);               // ds (bf16, TMEM) x W.e (bf16)
+          constexpr uint32_t idesc4 = make_idesc(128, 2 * TL, fmt_io);     // [dctx; h] x [a | ds], K-major over pixels
+          constexpr int ks1 = C >> 4;
+          const uint64_t d_ones = make_desc_sw128_mn_lbo(smem_u32(sOnes), 2048u);
+          const uint64_t d_bias = make_desc_sw128(smem_u32(sBias));
+          tc_fence_after();
+          int j1 = 0, j2 = 0;
+          while (j2 < ntile) {
+            const int i1 = it0 + j1, i2 = it0 + j2;
+            if (j1 < ntile && j1 < j2 + 2 && mbar_try_wait(&in_full[i1 % nst], (i1 / nst) & 1)) {
+              const int u = i1 & 1;
+              tc_fence_after();
+              const uint32_t st = smem_u32(sIn + (i1 % nst) * stage_bytes);
+              umma_f16(tmem + u * 96, d_ones, d_bias, idesc1, 0u);        // S = 0 / -inf per word
 #pragma unroll
-      for (int kk = 0; kk < C / 8; ++kk) {
-        uint32_t r[4];
+              for (int kk = 0; kk < ks1; ++kk) {
+                const uint64_t dh_ = make_desc_sw128_mn_lbo(st + box + kk * 2048, (uint32_t)(2 * box));    // h
+                const uint64_t dd_ = make_desc_sw128_mn_lbo(st + kk * 2048, (uint32_t)(2 * box));          // dctx
+                umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s)) + 2 * kk, idesc1, 1u);
+                umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s + NT * 128)) + 2 * kk, idesc1, 1u);
+                umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u)) + 2 * kk, idesc1, kk ? 1u : 0u);
+                umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u + NT * 128)) + 2 * kk, idesc1, 1u);
+              }
+              umma_commit(&s_full[u]);
+              ++j1;
+            }
+            if (j2 < j1 && mbar_try_wait(&p_ready[i2 & 1], (i2 >> 1) & 1) &&
+                (i2 < 2 || mbar_try_wait(&dh_empty[i2 & 1], ((i2 - 2) >> 1) & 1))) {
+              const int u = i2 & 1, s = i2 % nst;
+              tc_fence_after();
 #pragma unroll
-        for (int m = 0; m < 4; ++m) r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
-        stsm_x4_trans(sd.st + kk * 1024, r[0], r[1], r[2], r[3]);
-      }
-      __syncwarp();
-      const int pix = (tile0 + it) * 128 + sd.pxc;
-      IO* dst = dh + (size_t)sd.row * p.HW + pix;
+              for (int kk = 0; kk < NT / 16; ++kk) {      // dh = ds (hi + lo) x W.e (hi + lo), lo*lo dropped
+                const uint32_t a_hi = tmem + u * 96 + kk * 8, a_lo = tmem + u * 96 + 16 + kk * 8;
+                const uint64_t b_hi = make_desc_sw128(smem_u32(sB2)) + 2 * kk;
+                const uint64_t b_lo = make_desc_sw128(smem_u32(sB2 + 32 * 128)) + 2 * kk;
+                umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_hi, idesc3, kk ? 1u : 0u);
+                umma_f16_ts(tmem + u * 96 + 2 * NT, a_lo, b_hi, idesc3, 1u);
+                umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_lo, idesc3, 1u);
+              }
+              umma_commit(&dh_full[u]);
+              const uint32_t st = smem_u32(sIn + s * stage_bytes);
+              const uint32_t bt = smem_u32(sBt + u * (2 * bt_box));
 #pragma unroll
-      for (int i = 0; i < C / 8; ++i) {
-        if (pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sd.ld + i * 1024);
-        dst += row8;
+              for (int j = 0; j < 2; ++j)                  // two chunks of 64 pixels
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16(tmem + kAccCol, make_desc_sw128(st + j * 2 * box) + 2 * kk,
+                           make_desc_sw128(bt + j * bt_box) + 2 * kk, idesc4, (j2 | j | kk) ? 1u : 0u);
+              umma_commit(&in_empty[s]);
+              ++j2;
+            }
+          }
+          umma_commit(acc_done);
+        }
+        __syncwarp();
+      } else if (warp < 10) {
+        // ===================== softmax warpgroup u: thread = pixel =====================
+        const int u = warp >= 6 ? 1 : 0;
+        const IO* dattn = p.dattn ? (const IO*)p.dattn + (size_t)b * p.T * p.HW : nullptr;
+        const uint32_t bt_st = stage_addr(smem_u32(sBt) + u * (2 * bt_box), 2 * TL, q, lane).st;
+        constexpr bool kHalfIO = std::is_same<IO, __half>::value;
+        for (int j = ((it0 & 1) == u ? 0 : 1); j < ntile; j += 2) {
+          const int it = it0 + j, k = it >> 1;
+          mbar_wait(&s_full[u], k & 1);
+          tc_fence_after();
+          float s[TL], g[TL];
+          tmem_ld_cols<TL>(tmem + lane0 + u * 96, s);
+          tmem_ld_cols<TL>(tmem + lane0 + u * 96 + NT, g);
+          tmem_ld_wait();
+          float mx = fmaxf(s[0], s[1]);
+#pragma unroll
+          for (int t = 2; t < TL; t += 2) mx = fmaxf(mx, fmaxf(s[t], s[t + 1]));
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int t = 0; t < TL; ++t) {
+            s[t] = exp2f(s[t] - mx);
+            s4[t & 3] += s[t];
+          }
+          const float inv = __fdividef(1.f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+          if (dattn != nullptr) {                      // rare: a gradient arrives through the attention maps too
+            const int pix = (sg.tile0 + j) * 128 + q * 32 + lane;
+#pragma unroll
+            for (int t = 0; t < TL; ++t)
+              if (t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)t * p.HW + pix]);
+          }
+          float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int t = 0; t < TL; ++t) {
+            s[t] *= inv;
+            d4[t & 3] = fmaf(s[t], g[t], d4[t & 3]);
+          }
+          const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+          uint32_t hi[NT / 2], lo[NT / 2], pa[TL / 2];
+          uint32_t ph[kHalfIO ? TL / 2 : 1];
+#pragma unroll
+          for (int t = 0; t < NT; t += 2) {
+            if (t < TL) {
+              const float d0 = s[t] * (g[t] - dot), d1 = s[t + 1] * (g[t + 1] - dot);
+              const uint32_t h2 = pack2<__nv_bfloat16>(d0, d1);
+              hi[t / 2] = h2;
+              lo[t / 2] = pack2<__nv_bfloat16>(d0 - __uint_as_float(h2 << 16), d1 - __uint_as_float(h2 & 0xffff0000u));
+              pa[t / 2] = pack2<IO>(s[t], s[t + 1]);
+              if constexpr (kHalfIO) ph[t / 2] = pack2<IO>(d0, d1);
+            } else {
+              hi[t / 2] = 0u;
+              lo[t / 2] = 0u;
+            }
+          }
+          tmem_st_n<NT / 2>(tmem + lane0 + u * 96, hi);
+          tmem_st_n<NT / 2>(tmem + lane0 + u * 96 + 16, lo);
+          tmem_st_n<TL / 2>(tmem + lane0 + u * 96 + 32, pa);
+          if constexpr (kHalfIO) tmem_st_n<TL / 2>(tmem + lane0 + u * 96 + 48, ph);
+          tmem_st_wait();
+          // read a and ds back as stmatrix fragments: [a | ds] transposed into the B operand of GEMM4
+          uint32_t fa[2][2 * KB], fd[2][2 * KB];
+          constexpr int kDsCol = kHalfIO ? 48 : 0;
+          tmem_ld_packed<KB>(tmem + lane0 + u * 96 + 32, fa[0]);
+          tmem_ld_packed<KB>(tmem + lane0 + kHalfLanes + u * 96 + 32, fa[1]);
+          tmem_ld_packed<KB>(tmem + lane0 + u * 96 + kDsCol, fd[0]);
+          tmem_ld_packed<KB>(tmem + lane0 + kHalfLanes + u * 96 + kDsCol, fd[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int kk = 0; kk < KB; ++kk) {
+            stsm_x4_trans(bt_st + kk * 1024, fa[0][2 * kk], fa[0][2 * kk + 1], fa[1][2 * kk], fa[1][2 * kk + 1]);
+            stsm_x4_trans(bt_st + TL * 128 + kk * 1024, fd[0][2 * kk], fd[0][2 * kk + 1], fd[1][2 * kk], fd[1][2 * kk + 1]);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[u]);
+        }
+      } else {
+        // ===================== dh warps =====================
+        const int px = q * 32 + lane;
+        const int dtid = (warp - 10) * 32 + lane;
+        IO* dh = (IO*)p.dh + (size_t)b * C * p.HW;
+        const StageAddr sd = stage_addr(smem_u32(sStD), C, q, lane);
+        const size_t row8 = (size_t)8 * p.HW;
+        for (int j = 0; j < ntile; ++j) {
+          const int it = it0 + j, u = it & 1, k = it >> 1;
+          mbar_wait(&dh_full[u], k & 1);
+          tc_fence_after();
+          float w[2][4 * (C / 8)];
+          tmem_ld_frag<C / 8>(tmem + lane0 + u * 96 + 2 * NT, w[0]);
+          tmem_ld_frag<C / 8>(tmem + lane0 + kHalfLanes + u * 96 + 2 * NT, w[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dh_empty[u]);
+#pragma unroll
+          for (int kk = 0; kk < C / 8; ++kk) {
+            uint32_t r[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+              r[m] = pack2<IO>(w[m >> 1][4 * kk + 2 * (m & 1)], w[m >> 1][4 * kk + 2 * (m & 1) + 1]);
+            stsm_x4_trans(sd.st + kk * 1024, r[0], r[1], r[2], r[3]);
+          }
+          __syncwarp();
+          const int pix = (sg.tile0 + j) * 128 + sd.pxc;
+          IO* dst = dh + (size_t)sd.row * p.HW + pix;
+#pragma unroll
+          for (int i = 0; i < C / 8; ++i) {
+            if (pix < p.HW) *reinterpret_cast<uint4*>(dst) = lds128(sd.ld + i * 1024);
+            dst += row8;
+          }
+          __syncwarp();
+        }
+        // ---- d(W.e) partial of this segment: part[b][slot], slot = index of this CTA among those of sample b ----
+        {
+          const long long first_cta = (((long long)b * p.tiles + 1) * gridDim.x + total - 1) / total - 1;
+          float* part = p.part + ((size_t)b * p.part_slots + (size_t)(blockIdx.x - first_cta)) * C * p.T;
+          float* sX = reinterpret_cast<float*>(sStD);          // [C][TL] exchange between the two row groups
+          mbar_wait(acc_done, seg & 1);
+          tc_fence_after();
+          float va[TL], vd[TL];
+          tmem_ld_cols<TL>(tmem + lane0 + kAccCol, va);         // rows of dctx x columns of a
+          tmem_ld_cols<TL>(tmem + lane0 + kAccCol + TL, vd);    // rows of h x columns of ds
+          tmem_ld_wait();
+          tc_fence_before();
+          named_bar_sync(2, 128);                               // staging reads of the last tile are done
+          if (px >= C && px < 2 * C) {
+#pragma unroll
+            for (int t = 0; t < TL; ++t) sX[(px - C) * TL + t] = vd[t];
+          }
+          named_bar_sync(2, 128);
+          if (px < C) {
+#pragma unroll
+            for (int t = 0; t < TL; ++t)
+              if (t < p.T) part[px * p.T + t] = va[t] + p.scale * sX[px * TL + t];
+          }
+          named_bar_sync(2, 128);
+          (void)dtid;
+        }
       }
-      __syncwarp();
-    }
-    // ---- d(W.e) partial of this CTA ----
-    float* part = p.part + ((size_t)b * p.ctas_per_sample + blockIdx.x) * C * p.T;
-    if (ntile > 0) {
-      mbar_wait(&acc_done, 0);
-      tc_fence_after();
-      float v[2 * NT];
-      tmem_ld32(tmem + lane0 + kAccCol, v);
-      tmem_ld32(tmem + lane0 + kAccCol + 32, v + 32);
-      tmem_ld_wait();
-      if (px < C) {
-        for (int t = 0; t < NT; ++t) sAcc[px * NT + t] = v[t];                       // rows of dctx x columns of a
-      } else if (px < 2 * C) {
-        for (int t = 0; t < NT; ++t) sAcc[C * NT + (px - C) * NT + t] = v[NT + t];   // rows of h x columns of ds
-      }
-      named_bar_sync(1, 128);
-      for (int i = tid; i < C * p.T; i += 128) {
-        const int c = i / p.T, t = i - c * p.T;
-        part[i] = sAcc[c * NT + t] + p.scale * sAcc[C * NT + c * NT + t];
-      }
-    } else {
-      for (int i = tid; i < C * p.T; i += 128) part[i] = 0.f;
+      // dh warps have seen the accumulator of the segment complete: every MMA that reads the operands is done
+      named_bar_sync(1, kWorkers);
+      it0 += ntile;
+      g += ntile;
     }
   }
   tc_fence_before();
@@ -854,17 +895,40 @@ int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dct
   return 1;
 }
 
-int word_attn_bwd_tc_ctas(int B, int HW) {
+// persistent grid of the backward kernel: 2 CTAs per SM, never more CTAs than tiles
+static int bwd_grid(int B, int HW) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long ctas = (long long)sms * 2;
+  if (const char* e = getenv("AGB_ATTN_BWD_CTAS")) ctas = std::max(1, atoi(e));   // tuning knob
+  return (int)std::min<long long>(ctas, (long long)B * cdiv(HW, 128));
+}
+
+// number of per-sample partial-sum slots the backward kernel may write: the CTAs whose tile range
+// overlaps one sample (ranges are floor(total/G) or one more tiles long)
+int word_attn_bwd_tc_ctas(int B, int HW) {
   const int tiles = cdiv(HW, 128);
-  if (const char* e = getenv("AGB_ATTN_BWD_CPS")) return std::max(1, std::min(tiles, atoi(e)));   // tuning knob
-  return std::max(1, std::min(cdiv(tiles, 2), std::max(1, (sms * 2) / B)));
+  const long long total = (long long)B * tiles;
+  const long long m = std::max<long long>(1, total / bwd_grid(B, HW));
+  return (int)std::min<long long>(tiles, (tiles - 1) / m + 2);
+}
+
+// dwe[b][i] = sum over the slots sample b really has (fixed order -> deterministic)
+__global__ void sum_range_partials_kernel(const float* __restrict__ part, int slots, int tiles, int G, long long total,
+                                          int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  const long long first = (((long long)b * tiles + 1) * G + total - 1) / total - 1;
+  const long long last = (((long long)(b + 1) * tiles) * G + total - 1) / total - 1;
+  const float* p = part + (size_t)b * slots * n + i;
+  float acc = 0.f;
+  for (int k = 0; k <= (int)(last - first); ++k) acc += p[(size_t)k * n];
+  out[(size_t)b * n + i] = acc;
 }
 
 int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
-                     void* dimages, float* part, int ctas_per_sample, int B, int C, int HW, int T, int io_dtype,
+                     void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
                      float scale, cudaStream_t st) {
   const bool bf = io_dtype == AGB_BF16;
   CUtensorMap mapH, mapD;
@@ -874,11 +938,18 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
   p.we = we; p.mask = mask; p.dattn = dattn; p.dh = dimages; p.part = part;
   p.B = B; p.C = C; p.HW = HW; p.T = T; p.scale = scale;
   p.tiles = cdiv(HW, 128);
-  p.ctas_per_sample = ctas_per_sample;
+  p.ctas_per_sample = 0;
+  p.part_slots = part_slots;
   const int NT = kBwdNT;
-  const int smem = kBwdStages * 4 * C * 128 + 4 * NT * 128 + 2 * 32 * 128 + 2 * 2 * (2 * NT) * 128 + 4096 + NT * 128 +
-                   2 * C * 128 + 1024;
-  dim3 grid(ctas_per_sample, B);
+  const int TL = (T + 7) / 8 * 8;
+  const int fixed = 4 * NT * 128 + 2 * 32 * 128 + 2 * 2 * (2 * TL) * 128 + 4096 + NT * 128 + 2 * C * 128 + 256;
+  // deepest input ring that still lets two CTAs share the SM's 227 KB (1 KB reserved per CTA)
+  int stages = ((227 * 1024) / 2 - 1024 - fixed) / (4 * C * 128);
+  stages = std::max(2, std::min(kMaxBwdStages, stages));
+  if (const char* e = getenv("AGB_ATTN_BWD_STAGES")) stages = std::max(2, std::min(kMaxBwdStages, atoi(e)));   // tuning knob
+  p.stages = stages;
+  const int smem = stages * 4 * C * 128 + fixed;
+  const int grid = bwd_grid(B, HW);
   const int slot = prof_begin(PROF_ATTN_BWD, st);
 #define AGB_ATTN_BWD_CASE2(TLV, CTV)                                                              \
   if (bf) {                                                                                       \
@@ -905,7 +976,10 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
 #undef AGB_ATTN_BWD_CASE2
 #undef AGB_ATTN_BWD_CASE
   prof_end(slot, st);
-  return check_launch("word_attn_bwd_tc_kernel");
+  if (int rc = check_launch("word_attn_bwd_tc_kernel")) return rc;
+  sum_range_partials_kernel<<<dim3(cdiv(C * T, 128), B), 128, 0, st>>>(part, part_slots, p.tiles, grid,
+                                                                       (long long)B * p.tiles, C * T, dwe);
+  return check_launch("sum_range_partials_kernel");
 }
 
 // 1 when the tensor-core kernel can take this problem

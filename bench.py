@@ -9,7 +9,7 @@ One "step" is one pass of the hot path over one batch of synthetic input:
                          T=18, D=256 (grads w.r.t. region features, word embeddings, both codes)
   cfg4 (default at N>1)  the same step at global batch 2048 sharded over the N ranks (word features
                          all-gathered over NCCL so the negatives span the global batch); strong scaling
-  cfg3 / cfg1            generator word attention forward+backward (bf16 B=64 128x128 / fp32 B=16 64x64)
+  cfg3 / cfg1            generator word attention forward+backward (bf16 B=64, stages 64x64+128x128+256x256 / fp32 B=16 64x64)
 Metric: pairs/s (image-caption pairs) for the DAMSM step, pixels/s for the attention workloads.
 
 `value` is measured with inputs resident in HBM; `e2e` through the public drop-in API with pinned
@@ -290,53 +290,71 @@ def run_native(args):
         dtype = {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.math]
     else:
         if args.workload == "cfg1":
-            B, C, E, T, hw, tdt = 16, 32, 256, 18, 64, torch.float32
+            B, C, E, T, hws, tdt = 16, 32, 256, 18, [64], torch.float32
         else:
-            B, C, E, T, hw, tdt = 64, 32, 256, 18, 128, torch.bfloat16
+            # configs[2]: the generator's attention stages, 64x64 and 128x128 (generator.py:56,61) plus the
+            # synthetic 256x256 third stage of SURVEY 8d; one step = forward + backward of every stage
+            B, C, E, T, hws, tdt = 64, 32, 256, 18, [64, 128, 256], torch.bfloat16
+        if args.hw:
+            hws = [args.hw]
         B = args.batch or B
         assert B % world == 0
         Bl = B // world
-        images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed=0)
         sl = slice(rank * Bl, rank * Bl + Bl)
         g = torch.Generator().manual_seed(1)
-        img_h = images[sl].to(tdt).contiguous().pin_memory()
-        dctx_h = torch.randn(B, C, hw, hw, generator=g)[sl].to(tdt).contiguous().pin_memory()
+        img_h, dctx_h = [], []
+        for hw in hws:
+            images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed=0)
+            img_h.append(images[sl].to(tdt).contiguous().pin_memory())
+            dctx_h.append(torch.randn(B, C, hw, hw, generator=g)[sl].to(tdt).contiguous().pin_memory())
+            del images
         wrd_h = words[sl].transpose(1, 2).contiguous().pin_memory()        # physical [B,T,E]
         mask_d = mask[sl].to(dev)
-        mod = pkg.AttentionModule(C, E).to(dev)
-        with torch.no_grad():
-            mod.conv1.weight.copy_(weight.to(dev))
-        mod.apply_mask(mask_d)
-        out_h = torch.empty(256, dtype=tdt).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in (img_h, dctx_h, wrd_h))
+        mods = []
+        for hw in hws:                                                      # one AttentionModule per stage
+            mod = pkg.AttentionModule(C, E).to(dev)
+            with torch.no_grad():
+                mod.conv1.weight.copy_(weight.to(dev))
+            mod.apply_mask(mask_d)
+            mods.append(mod)
+        out_h = torch.empty(256 * len(hws), dtype=tdt).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in (*img_h, *dctx_h, wrd_h))
         d2h = out_h.numel() * out_h.element_size()
 
         def make_dev():
-            return [img_h.to(dev).requires_grad_(True), wrd_h.to(dev).requires_grad_(True), dctx_h.to(dev)]
+            return [[t.to(dev).requires_grad_(True) for t in img_h], wrd_h.to(dev).requires_grad_(True),
+                    [t.to(dev) for t in dctx_h]]
 
         def step_dev(ts):
-            im, wd, dctx = ts
-            im.grad = None
+            ims, wd, dctxs = ts
             wd.grad = None
-            mod.conv1.weight.grad = None
-            ctx, attn = mod(im, wd.transpose(1, 2))
-            ctx.backward(dctx)
-            return ctx, attn
+            outs = []
+            for mod, im, dctx in zip(mods, ims, dctxs):
+                im.grad = None
+                mod.conv1.weight.grad = None
+                ctx, attn = mod(im, wd.transpose(1, 2))
+                ctx.backward(dctx)
+                outs.append((ctx, attn))
+            return outs
 
         def step_e2e():
-            im = img_h.to(dev, non_blocking=True).requires_grad_(True)
             wd = wrd_h.to(dev, non_blocking=True).requires_grad_(True)
-            dctx = dctx_h.to(dev, non_blocking=True)
-            mod.conv1.weight.grad = None
-            ctx, attn = mod(im, wd.transpose(1, 2))
-            ctx.backward(dctx)
-            out_h.copy_(im.grad.reshape(-1)[:256], non_blocking=True)   # read a slice of the step's result back
+            for i, (mod, im_h, dc_h) in enumerate(zip(mods, img_h, dctx_h)):
+                im = im_h.to(dev, non_blocking=True).requires_grad_(True)
+                dctx = dc_h.to(dev, non_blocking=True)
+                mod.conv1.weight.grad = None
+                ctx, attn = mod(im, wd.transpose(1, 2))
+                ctx.backward(dctx)
+                # read a slice of every stage's result back
+                out_h[256 * i:256 * (i + 1)].copy_(im.grad.reshape(-1)[:256], non_blocking=True)
 
-        units = Bl * hw * hw
-        total_units = B * hw * hw
+        npix = sum(hw * hw for hw in hws)
+        units = Bl * npix
+        total_units = B * npix
         es = 4 if tdt == torch.float32 else 2
         metric, unit = "word_attention_fwd_bwd_pixels_per_sec", "pixels/s"
-        workload = (f"{args.workload}: AttentionModule fwd+bwd, batch {B}, {hw}x{hw} feature map, T={T}, C={C}, E={E}, "
+        workload = (f"{args.workload}: AttentionModule fwd+bwd, batch {B}, feature maps "
+                    f"{' + '.join('%dx%d' % (hw, hw) for hw in hws)}, T={T}, C={C}, E={E}, "
                     f"{'fp32' if es == 4 else 'bf16'} I/O")
         bytes_fwd, bytes_bwd = es * (2 * C + T), es * 3 * C
         tags = [4, 5]
@@ -434,7 +452,7 @@ def run_native(args):
         gb = (bytes_fwd + bytes_bwd) * units * prof_steps / 1e9
         ach = gb / ((ms_f + ms_b) * 1e-3) if ms_f + ms_b > 0 else 0.0
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                "traffic": load_traffic(args.workload) if args.batch is None else None,
+                "traffic": load_traffic(args.workload) if (args.batch is None and args.hw is None) else None,
                 "kernel": "word_attn_fwd(_tc)_kernel + word_attn_bwd(_tc)_kernel",
                 "launches": int(n_f + n_b), "avg_launch_ms": (ms_f + ms_b) / max(n_f + n_b, 1),
                 "fwd_gbs": bytes_fwd * units * prof_steps / 1e9 / (ms_f * 1e-3) if ms_f > 0 else None,
@@ -480,6 +498,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--math", default=None, choices=["fp32", "f16", "bf16"])
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--hw", type=int, default=None, help="attention workloads: a single feature-map side instead of the config's stages")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -115,21 +115,21 @@ __global__ void ce_grad_kernel(const float* __restrict__ raw, int B, const int32
 }
 
 // Whole two-way CE in one CTA for B <= 128 (the reference's batch sizes: 16-64): logits live in
-// shared memory, warp w folds rows w, w+8, ... and then columns w, w+8, ... with the same in-order
+// shared memory, warp w folds rows w, w+32, ... and then columns w, w+32, ... with the same in-order
 // merges as the multi-kernel path, loss and the requested gradient rows come out of the same launch.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 ce_small_kernel(const float* __restrict__ raw, int B, const int32_t* __restrict__ cls,
                 const int64_t* __restrict__ labels, float gamma3, float lambda, int row_begin, int row_count,
                 float* __restrict__ loss_out, float* __restrict__ draw) {
   extern __shared__ float lg[];                 // [B][B+1] logits
   __shared__ float lse_r[128], lse_c[128], part[256];
-  const int P = B + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int P = B + 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) {
     const int a = i / B, b = i - a * B;
     lg[a * P + b] = logit_at(raw, cls, B, a, b, gamma3);
   }
   __syncthreads();
-  for (int a = warp; a < B; a += 8) {           // rows
+  for (int a = warp; a < B; a += nw) {          // rows
     float m = -INFINITY, s = 0.f;
     for (int b = lane; b < B; b += 32) lse_push(m, s, lg[a * P + b]);
 #pragma unroll
@@ -142,7 +142,7 @@ ce_small_kernel(const float* __restrict__ raw, int B, const int32_t* __restrict_
       part[a] = lse_r[a] - lg[a * P + (int)labels[a]];
     }
   }
-  for (int b = warp; b < B; b += 8) {           // columns
+  for (int b = warp; b < B; b += nw) {          // columns
     float m = -INFINITY, s = 0.f;
     for (int a = lane; a < B; a += 32) lse_push(m, s, lg[a * P + b]);
 #pragma unroll
@@ -320,7 +320,7 @@ extern "C" int agb_contrastive_fwd(const float* raw, int B, const int32_t* class
   if (B <= 128) {
     const size_t smem = (size_t)B * (B + 1) * sizeof(float);
     if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(ce_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ce_small_kernel<<<1, 256, smem, st>>>(raw, B, class_ids, labels, gamma3, lambda, row_begin, row_count, loss_out,
+    ce_small_kernel<<<1, 1024, smem, st>>>(raw, B, class_ids, labels, gamma3, lambda, row_begin, row_count, loss_out,
                                           row_count > 0 ? draw : nullptr);
     return check_launch("ce_small_kernel");
   }

@@ -12,6 +12,8 @@
 //
 // and for backward additionally G [Bi,N,R] (d beta, then the dW operand) and per-word scalars.
 // All contractions go through sgemm_strided (fixed summation order, no atomics).
+#include <algorithm>
+#include <cooperative_groups.h>
 #include "agb_common.cuh"
 
 namespace agb {
@@ -546,19 +548,27 @@ static int func_scores(const float* query, int64_t qs_b, int64_t qs_d, int64_t q
 // WordsLoss (words_loss.py:63) for the tensor-core path.  One block per image, thread = region:
 // scores over the feature dim with the caption's words broadcast from shared memory, both softmaxes
 // in registers (S, Bt: unused scratch kept for ABI stability of the internal call).
-template <int TMAX, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+// The feature dimension is split over the CTAs of a thread-block cluster (blockIdx.y = slice): every CTA
+// accumulates the raw scores of its slice, the partial sums meet in the leader through distributed
+// shared memory in a fixed order, and the leader finishes the two softmaxes.
+template <int TMAX>
+__global__ void __launch_bounds__(1024)
 diag_att_kernel(const float* __restrict__ img, const float* __restrict__ words, int64_t ws_b, int64_t ws_d,
                 int64_t ws_t, const int32_t* __restrict__ cap_lens, int T, int D, int R, float inv_sqrt_d,
                 float gamma1, int row_offset, float* __restrict__ att_out) {
-  extern __shared__ float w_s[];                  // [D][TMAX]
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float w_s[];                  // [slice of D][TMAX] words, then [TMAX][blockDim.x] partial scores
+  const int parts = gridDim.y, part = blockIdx.y, tpr = blockDim.x;
+  const int d0 = (int)((long long)D * part / parts), d1 = (int)((long long)D * (part + 1) / parts);
+  float* acc_s = w_s + (size_t)((D + parts - 1) / parts + 1) * TMAX;
   __shared__ float red_s[32 * TMAX];
   __shared__ float z_s[TMAX];
   const int b = blockIdx.x, r = threadIdx.x, i = row_offset + b;
   const int L = min(max(cap_lens[i], 0), T);
-  for (int k = threadIdx.x; k < D * TMAX; k += blockDim.x) {
+  for (int k = threadIdx.x; k < (d1 - d0) * TMAX; k += blockDim.x) {
     const int d = k / TMAX, t = k - d * TMAX;
-    w_s[k] = (t < L) ? words[(int64_t)i * ws_b + (int64_t)d * ws_d + (int64_t)t * ws_t] : 0.f;
+    w_s[k] = (t < L) ? words[(int64_t)i * ws_b + (int64_t)(d0 + d) * ws_d + (int64_t)t * ws_t] : 0.f;
   }
   __syncthreads();
   const bool live = r < R;
@@ -566,8 +576,9 @@ diag_att_kernel(const float* __restrict__ img, const float* __restrict__ words, 
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) e[t] = 0.f;
   if (live) {
-    const float* c = img + (size_t)b * D * R + r;
-    for (int d = 0; d < D; ++d) {
+    const float* c = img + (size_t)b * D * R + (size_t)d0 * R + r;
+#pragma unroll 8
+    for (int d = 0; d < d1 - d0; ++d) {
       const float cv = c[(size_t)d * R];
       const float4* w4 = reinterpret_cast<const float4*>(w_s + d * TMAX);
 #pragma unroll
@@ -580,6 +591,20 @@ diag_att_kernel(const float* __restrict__ img, const float* __restrict__ words, 
       }
     }
   }
+  if (part > 0) {
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) acc_s[t * tpr + r] = e[t];
+  }
+  cluster.sync();
+  if (part == 0) {
+    for (int pp = 1; pp < parts; ++pp) {           // fixed order -> deterministic
+      const float* remote = cluster.map_shared_rank(acc_s, pp);
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t) e[t] += remote[t * tpr + r];
+    }
+  }
+  cluster.sync();                                  // the slices' shared memory stays alive until it has been read
+  if (part > 0) return;
   float mx = -INFINITY;
 #pragma unroll
   for (int t = 0; t < TMAX; ++t)
@@ -609,20 +634,29 @@ int damsm_diag_att_maps(const float* img, const float* words, int64_t ws_b, int6
                         float* att_out, float* S, float* Bt, cudaStream_t st) {
   (void)S;
   (void)Bt;
-  const int threads = (R + 31) / 32 * 32;
+  const int tpr = (R + 31) / 32 * 32;
+  if (tpr > 1024) return fail_unsupported("R=%d regions > 1024", R);
+  const int parts = D >= 64 ? 4 : 1;              // cluster size: slices of the feature dimension
   const float isd = 1.f / sqrtf((float)D);
   const int tm = pick_tmax(T);
-  const size_t smem = (size_t)D * tm * sizeof(float);
+  const size_t smem = ((size_t)((D + parts - 1) / parts + 1) * tm + (size_t)tm * tpr) * sizeof(float);
   AGB_TMAX_SWITCH(tm, {
-    if (threads <= 352) {
-      auto kern = diag_att_kernel<TMAX, 352>;
-      if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<Bi, threads, smem, st>>>(img, words, ws_b, ws_d, ws_t, cap_lens, T, D, R, isd, gamma1, row_offset, att_out);
-    } else {
-      auto kern = diag_att_kernel<TMAX, 1024>;
-      if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<Bi, threads, smem, st>>>(img, words, ws_b, ws_d, ws_t, cap_lens, T, D, R, isd, gamma1, row_offset, att_out);
-    }
+    auto kern = diag_att_kernel<TMAX>;
+    if (smem > 48 * 1024) AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Bi, parts);
+    cfg.blockDim = dim3(tpr);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = parts;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AGB_CUDA(cudaLaunchKernelEx(&cfg, kern, img, words, ws_b, ws_d, ws_t, cap_lens, T, D, R, isd, gamma1, row_offset,
+                                att_out));
   });
   return check_launch("diag_att_kernel");
 }

@@ -84,7 +84,8 @@ def test_tc_similarity_matrix_matches_oracle(agb, math, tol, B, full, trained):
     assert err < tol, f"max |m - ref| = {err:.3e}"
     # matched-pair attention maps come from the fp32 kernels even in tensor-core mode
     m32, att32, _ = ops.damsm_fwd(img3, wrd.cuda(), lens.cuda().to(torch.int32), 4.0, 5.0, 1e-8, 0, True, 0)
-    assert torch.equal(att, att32)
+    # both are fp32 kernels; they sum the 256 feature products in a different (each fixed) order
+    torch.testing.assert_close(att, att32, rtol=1e-5, atol=1e-8)
     assert (m - m32).abs().max().item() < tol
 
 

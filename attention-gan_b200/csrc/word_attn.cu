@@ -10,6 +10,7 @@
 //
 // Algorithmic HBM bytes per pixel (es = bytes per element): fwd es*(2C+T), bwd es*3C (+es*T with
 // dattn); see DESIGN.md.
+#include <algorithm>
 #include "agb_common.cuh"
 
 namespace agb {
@@ -21,6 +22,7 @@ int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, v
 int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dctx_bs, const void* dattn, int C, int HW,
                                int T, int io_dtype);
 int word_attn_bwd_tc_ctas(int B, int HW);
+int word_attn_bwd_tc_grid(int B, int HW);
 int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
                      void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
                      float scale, cudaStream_t st);
@@ -406,6 +408,7 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int nparts, 
   if (i >= n) return;
   const float* p = part + (int64_t)b * batch_stride + i;
   float acc = 0.f;
+#pragma unroll 8
   for (int k = 0; k < nparts; ++k) acc += p[(int64_t)k * part_stride];
   out[(size_t)b * n + i] = acc;
 }
@@ -424,6 +427,102 @@ __global__ void word_attn_bwd_dw_kernel(const float* __restrict__ dwe, const flo
     for (int t = 0; t < T; ++t) acc = fmaf(d[t], x[(int64_t)t * ws_t], acc);
   }
   dconv_w[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small per-sample kernels around the pixel kernels (the conv1 projection and its autograd);
+// one CTA per sample, everything staged in shared memory, fixed summation orders
+// ---------------------------------------------------------------------------------------------
+// we[b][c,t] = sum_e W[c,e] words[b][e,t]                              (attention.py:50-52, conv1 1x1)
+// thread = one output (c, t); W and the sample's words sit in shared memory with padded rows
+__device__ __forceinline__ void stage_words(float* x_s, const float* __restrict__ words, int64_t ws_b, int64_t ws_e,
+                                            int64_t ws_t, int b, int E, int T) {
+#pragma unroll 8
+  for (int i = threadIdx.x; i < E * T; i += blockDim.x) {
+    // walk the source along its contiguous dimension
+    const int e = ws_e == 1 ? i % E : i / T, t = ws_e == 1 ? i / E : i % T;
+    x_s[t * (E + 1) + e] = words[(int64_t)b * ws_b + (int64_t)e * ws_e + (int64_t)t * ws_t];
+  }
+}
+__global__ void __launch_bounds__(1024)
+project_words_kernel(const float* __restrict__ conv_w, const float* __restrict__ words, int64_t ws_b, int64_t ws_e,
+                     int64_t ws_t, float* __restrict__ we, int C, int E, int T) {
+  extern __shared__ float sm_[];
+  float* w_s = sm_;                               // [C][E + 1]
+  float* x_s = sm_ + (size_t)C * (E + 1);         // [T][E + 1]
+  const int b = blockIdx.x, P = E + 1;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < C * E; i += blockDim.x) w_s[(i / E) * P + (i % E)] = conv_w[i];
+  stage_words(x_s, words, ws_b, ws_e, ws_t, b, E, T);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    const float* w = w_s + c * P;
+    const float* x = x_s + t * P;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int e = 0;
+    for (; e + 4 <= E; e += 4) {
+      a0 = fmaf(w[e], x[e], a0);
+      a1 = fmaf(w[e + 1], x[e + 1], a1);
+      a2 = fmaf(w[e + 2], x[e + 2], a2);
+      a3 = fmaf(w[e + 3], x[e + 3], a3);
+    }
+    for (; e < E; ++e) a0 = fmaf(w[e], x[e], a0);
+    we[(size_t)b * C * T + i] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+// backward of the projection for one sample: dwe[b] = sum of the pixel kernel's partial slots;
+// dwords[b][e,t] = sum_c W[c,e] dwe[b][c,t];  dwp[b][c,e] = sum_t dwe[b][c,t] words[b][e,t]
+// (this sample's share of d conv1.weight; summed over b by sum_partials_kernel).
+// slot count: G == 0: `slots` (every slot valid); G > 0: the CTAs of a persistent grid of G whose tile
+// range overlaps sample b (word_attn_tc.cu).  thread = embedding index e.
+__global__ void __launch_bounds__(1024)
+project_words_bwd_kernel(const float* __restrict__ part, int slots, int tiles, int G, long long total,
+                         const float* __restrict__ conv_w, const float* __restrict__ words, int64_t ws_b,
+                         int64_t ws_e, int64_t ws_t, float* __restrict__ dwe, float* __restrict__ dwords,
+                         float* __restrict__ dwp, int C, int E, int T) {
+  extern __shared__ float sm_[];
+  const int b = blockIdx.x, P = E + 1;
+  float* d_s = sm_;                               // [C][T]
+  float* w_s = d_s + C * T;                       // [C][E + 1]
+  float* x_s = w_s + (size_t)C * P;               // [T][E + 1]
+  int n = slots;
+  if (G > 0) {
+    const long long first = (((long long)b * tiles + 1) * G + total - 1) / total - 1;
+    const long long last = (((long long)(b + 1) * tiles) * G + total - 1) / total - 1;
+    n = (int)(last - first) + 1;
+  }
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const float* p = part + (size_t)b * slots * C * T + i;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) acc += p[(size_t)k * C * T];
+    d_s[i] = acc;
+    dwe[(size_t)b * C * T + i] = acc;
+  }
+  if (dwords != nullptr) {
+#pragma unroll 8
+    for (int i = threadIdx.x; i < C * E; i += blockDim.x) w_s[(i / E) * P + (i % E)] = conv_w[i];
+  }
+  if (dwp != nullptr) stage_words(x_s, words, ws_b, ws_e, ws_t, b, E, T);
+  __syncthreads();
+  if (dwords != nullptr) {
+    for (int i = threadIdx.x; i < E * T; i += blockDim.x) {      // lanes = consecutive e: conflict-free
+      const int t = i / E, e = i - t * E;
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) acc = fmaf(w_s[c * P + e], d_s[c * T + t], acc);
+      dwords[((size_t)b * E + e) * T + t] = acc;
+    }
+  }
+  if (dwp != nullptr) {
+    for (int i = threadIdx.x; i < C * E; i += blockDim.x) {
+      const int c = i / E, e = i - c * E;
+      float acc = 0.f;
+      for (int t = 0; t < T; ++t) acc = fmaf(d_s[c * T + t], x_s[t * P + e], acc);
+      dwp[((size_t)b * C + c) * E + e] = acc;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -513,13 +612,15 @@ extern "C" int agb_word_attn_fwd(const void* images, const float* words, int64_t
   if (int rc = check_common(B, C, HW, E, T, io_dtype)) return rc;
   if (!images || !words || !conv_w || !mask || !ctx || !we) return fail_arg("null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  {  // we[b][c,t] = sum_e W[c,e] words[b][e,t]                     (attention.py:50-52, conv1 1x1)
-    SgemmArgs g{};
-    g.A = conv_w; g.a_m = E; g.a_k = 1; g.a_batch = 0;
-    g.B = words; g.b_k = ws_e; g.b_n = ws_t; g.b_batch = ws_b;
-    g.C = we; g.c_m = T; g.c_n = 1; g.c_batch = (int64_t)C * T;
-    g.M = C; g.N = T; g.K = E; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
-    if (int rc = sgemm_strided(g, B, st)) return rc;
+  // we[b][c,t] = sum_e W[c,e] words[b][e,t]                     (attention.py:50-52, conv1 1x1)
+  {
+    const size_t smem = (size_t)(C + T) * (E + 1) * sizeof(float);
+    if (smem > 200 * 1024) return fail_unsupported("E=%d is outside the compiled range of the projection kernel", E);
+    if (smem > 48 * 1024)
+      AGB_CUDA(cudaFuncSetAttribute(project_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = std::min(1024, (C * T + 31) / 32 * 32);
+    project_words_kernel<<<B, threads, smem, st>>>(conv_w, words, ws_b, ws_e, ws_t, we, C, E, T);
+    if (int rc = check_launch("project_words_kernel")) return rc;
   }
   const float qscale = (scaled ? 1.f / sqrtf((float)C) : 1.f) * kLog2e;
   // 16-bit feature maps: both contractions on tcgen05 (word_attn_tc.cu); fp32 maps and odd shapes:
@@ -548,7 +649,7 @@ static int dw_splits(int B) {
 extern "C" size_t agb_word_attn_bwd_workspace_bytes(int B, int C, int HW, int E, int T) {
   if (B <= 0 || C <= 0 || HW <= 0 || E <= 0 || T <= 0 || T > 64) return 0;
   const size_t ntiles = cdiv(HW, 128);   // upper bound of the partial sums either kernel family writes
-  return (((size_t)B * ntiles + (size_t)B) * C * T + (size_t)dw_splits(B) * C * E) * sizeof(float);
+  return (((size_t)B * ntiles + (size_t)B) * C * T + (size_t)B * C * E) * sizeof(float);
 }
 
 extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t ws_b, int64_t ws_e,
@@ -574,9 +675,10 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
   const bool use_tc = tc::word_attn_bwd_tc_supported(images, dctx, dctx_bs, dattn, C, HW, T, io_dtype) != 0;
   if (use_tc) ntiles = tc::word_attn_bwd_tc_ctas(B, HW);
   float* dwe = part + (size_t)B * ntiles * C * T;
+  int G = 0;                                      // 0: every partial slot is valid
   if (use_tc) {
-    // tensor-core kernel + its own reduction of the per-CTA partials into dwe
-    rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dattn, dimages, part, ntiles, dwe, B, C, HW, T, io_dtype, scale, st);
+    G = tc::word_attn_bwd_tc_grid(B, HW);
+    rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dattn, dimages, part, ntiles, nullptr, B, C, HW, T, io_dtype, scale, st);
     if (rc) return rc;
   } else {
     AGB_DISPATCH_TMAX(tm, {
@@ -586,30 +688,20 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
       else rc = launch_bwd<__half, TMAX, VV>(images, we, mask, dctx, dctx_bs, dattn, dimages, part, B, C, HW, T, scale, use_tma, st);
     });
     if (rc) return rc;
-    // dwe[b] = sum of the partials
-    sum_partials_kernel<<<dim3(cdiv(C * T, 128), B), 128, 0, st>>>(part, ntiles, (int64_t)C * T, (int64_t)ntiles * C * T,
-                                                                   C * T, dwe);
-    if ((rc = check_launch("sum_partials_kernel"))) return rc;
   }
-  // dwords[b][e,t] = sum_c W[c,e] dwe[b][c,t]; dW[c,e] = sum_b,t dwe[b][c,t] words[b][e,t]
-  if (dwords) {
-    SgemmArgs g{};
-    g.A = conv_w; g.a_m = 1; g.a_k = E; g.a_batch = 0;
-    g.B = dwe; g.b_k = T; g.b_n = 1; g.b_batch = (int64_t)C * T;
-    g.C = dwords; g.c_m = T; g.c_n = 1; g.c_batch = (int64_t)E * T;
-    g.M = E; g.N = T; g.K = C; g.KB = 1; g.alpha = 1.f; g.accumulate = 0;
-    if ((rc = sgemm_strided(g, B, st))) return rc;
-  }
+  // one CTA per sample: dwe[b] = sum of the partial slots; dwords[b][e,t] = sum_c W[c,e] dwe[b][c,t];
+  // dwp[b][c,e] = sum_t dwe[b][c,t] words[b][e,t]; then dW[c,e] = sum_b dwp[b][c,e] in a fixed order
+  float* dwp = dwe + (size_t)B * C * T;
+  const size_t psmem = ((size_t)C * T + (size_t)(C + T) * (E + 1)) * sizeof(float);
+  if (psmem > 200 * 1024) return fail_unsupported("E=%d is outside the compiled range of the projection kernel", E);
+  if (psmem > 48 * 1024)
+    AGB_CUDA(cudaFuncSetAttribute(project_words_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+  project_words_bwd_kernel<<<B, 1024, psmem, st>>>(
+      part, ntiles, cdiv(HW, 128), G, (long long)B * cdiv(HW, 128), conv_w, words, ws_b, ws_e, ws_t, dwe, dwords,
+      dconv_w ? dwp : nullptr, C, E, T);
+  if ((rc = check_launch("project_words_bwd_kernel"))) return rc;
   if (dconv_w) {
-    const int S = dw_splits(B), per = B / S;
-    float* dwp = dwe + (size_t)B * C * T;
-    SgemmArgs g{};
-    g.A = dwe; g.a_m = T; g.a_k = 1; g.a_kb = (int64_t)C * T; g.a_batch = (int64_t)per * C * T;
-    g.B = words; g.b_k = ws_t; g.b_n = ws_e; g.b_kb = ws_b; g.b_batch = (int64_t)per * ws_b;
-    g.C = dwp; g.c_m = E; g.c_n = 1; g.c_batch = (int64_t)C * E;
-    g.M = C; g.N = E; g.K = T; g.KB = per; g.alpha = 1.f; g.accumulate = 0;
-    if ((rc = sgemm_strided(g, S, st))) return rc;
-    sum_partials_kernel<<<dim3(cdiv(C * E, 128), 1), 128, 0, st>>>(dwp, S, (int64_t)C * E, 0, C * E, dconv_w);
+    sum_partials_kernel<<<dim3(cdiv(C * E, 128), 1), 128, 0, st>>>(dwp, B, (int64_t)C * E, 0, C * E, dconv_w);
     if ((rc = check_launch("sum_partials_kernel"))) return rc;
   }
   return 0;

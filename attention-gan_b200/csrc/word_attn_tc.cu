@@ -896,7 +896,7 @@ int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dct
 }
 
 // persistent grid of the backward kernel: 2 CTAs per SM, never more CTAs than tiles
-static int bwd_grid(int B, int HW) {
+int word_attn_bwd_tc_grid(int B, int HW) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -910,7 +910,7 @@ static int bwd_grid(int B, int HW) {
 int word_attn_bwd_tc_ctas(int B, int HW) {
   const int tiles = cdiv(HW, 128);
   const long long total = (long long)B * tiles;
-  const long long m = std::max<long long>(1, total / bwd_grid(B, HW));
+  const long long m = std::max<long long>(1, total / word_attn_bwd_tc_grid(B, HW));
   return (int)std::min<long long>(tiles, (tiles - 1) / m + 2);
 }
 
@@ -949,7 +949,7 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
   if (const char* e = getenv("AGB_ATTN_BWD_STAGES")) stages = std::max(2, std::min(kMaxBwdStages, atoi(e)));   // tuning knob
   p.stages = stages;
   const int smem = stages * 4 * C * 128 + fixed;
-  const int grid = bwd_grid(B, HW);
+  const int grid = word_attn_bwd_tc_grid(B, HW);
   const int slot = prof_begin(PROF_ATTN_BWD, st);
 #define AGB_ATTN_BWD_CASE2(TLV, CTV)                                                              \
   if (bf) {                                                                                       \
@@ -977,6 +977,7 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
 #undef AGB_ATTN_BWD_CASE
   prof_end(slot, st);
   if (int rc = check_launch("word_attn_bwd_tc_kernel")) return rc;
+  if (dwe == nullptr) return 0;                   // the caller reduces the partial slots itself
   sum_range_partials_kernel<<<dim3(cdiv(C * T, 128), B), 128, 0, st>>>(part, part_slots, p.tiles, grid,
                                                                        (long long)B * p.tiles, C * T, dwe);
   return check_launch("sum_range_partials_kernel");

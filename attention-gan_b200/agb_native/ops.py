@@ -97,10 +97,12 @@ def damsm_supported(T: int, D: int, R: int, math: int) -> bool:
 def damsm_fwd(img: torch.Tensor, words: torch.Tensor, cap_lens: torch.Tensor, gamma1: float,
               gamma2: float, eps: float = 1e-8, row_offset: int = 0, want_att: bool = True,
               math: int = N.AGB_MATH_FP32, cnn: Optional[torch.Tensor] = None,
-              rnn: Optional[torch.Tensor] = None, keep_ws: bool = False):
+              rnn: Optional[torch.Tensor] = None, keep_ws: bool = False, save: bool = False):
     """img [Bi,D,R] fp32 contiguous, words [Bc,D,T] fp32 (any strides), cap_lens [Bc] int32.
     Returns (m [Bi,Bc], att [Bi,T,R] or None, scos [Bi,Bc] or None); with keep_ws also the workspace
-    tensor, whose packed operands damsm_bwd(ws=...) can reuse."""
+    tensor, whose packed operands damsm_bwd(ws=...) can reuse.  save (tensor-core math only): the
+    training forward, which also leaves the normalised context vectors in the workspace so that
+    damsm_bwd(ws=..., ws_saved=True) does not recompute them."""
     require_cuda(img, words, cap_lens, cnn, rnn)
     Bi, D, R = img.shape
     Bc, _, T = words.shape
@@ -114,7 +116,8 @@ def damsm_fwd(img: torch.Tensor, words: torch.Tensor, cap_lens: torch.Tensor, ga
     ws = _ws(nbytes, dev)
     rc = N.lib().agb_damsm_fwd(_p(img), _p(words), words.stride(0), words.stride(1), words.stride(2),
                                _p(cap_lens), Bi, Bc, T, D, R, gamma1, gamma2, eps, row_offset, _p(m),
-                               _p(att), _p(cnn), _p(rnn), _p(scos), _p(ws), ws.numel(), math, _stream(img))
+                               _p(att), _p(cnn), _p(rnn), _p(scos), _p(ws), ws.numel(),
+                               math | (N.AGB_MATH_SAVE if save else 0), _stream(img))
     N.check(rc, "agb_damsm_fwd")
     if keep_ws:
         return m, att, scos, ws
@@ -123,8 +126,9 @@ def damsm_fwd(img: torch.Tensor, words: torch.Tensor, cap_lens: torch.Tensor, ga
 
 def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords: bool,
               math: int = N.AGB_MATH_FP32, m_fwd: Optional[torch.Tensor] = None,
-              ws: Optional[torch.Tensor] = None):
-    """dm [Bi,Bc] = dLoss/dm, gscale: device scalar or None.
+              ws: Optional[torch.Tensor] = None, ws_saved: bool = False):
+    """dm [Bi,Bc] = dLoss/dm, gscale: device scalar or None.  ws: the workspace of the matching damsm_fwd
+    call (ws_saved: that call ran with save=True).
     Returns (dimg [Bi,D,R], dwords [Bc,T,D] word-major or None)."""
     require_cuda(img, words, cap_lens, dm, gscale)
     Bi, D, R = img.shape
@@ -132,7 +136,7 @@ def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords
     dev = img.device
     dimg = torch.empty_like(img)
     dwords = torch.empty((Bc, T, D), dtype=torch.float32, device=dev) if need_dwords else None
-    from_fwd = int(ws is not None)
+    from_fwd = (2 if ws_saved else 1) if ws is not None else 0
     if ws is None:
         ws = _ws(N.lib().agb_damsm_workspace_bytes(Bi, Bc, T, D, R, math), dev)
     rc = N.lib().agb_damsm_bwd(_p(img), _p(words), words.stride(0), words.stride(1), words.stride(2),

@@ -21,7 +21,7 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1,
                  float gamma2, float eps, int row_offset, float* m_out, float* att_out,
                  const float* cnn, const float* rnn, float* scos_out, void* workspace,
-                 size_t workspace_bytes, int math, cudaStream_t st);
+                 size_t workspace_bytes, int math, int save, cudaStream_t st);
 int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1,
                  float gamma2, float eps, const float* dm, const float* m_fwd, const float* gscale, float* dimg,
@@ -49,6 +49,7 @@ extern "C" int agb_damsm_supported(int T, int D, int R, int math) {
 }
 
 extern "C" size_t agb_damsm_workspace_bytes(int Bi, int Bc, int T, int D, int R, int math) {
+  math &= ~AGB_MATH_SAVE;
   if (Bi <= 0 || Bc <= 0 || !agb_damsm_supported(T, D, R, math)) return 0;
   if (math == AGB_MATH_FP32) return damsm_fp32_workspace_bytes(Bi, Bc, T, D, R);
 #ifdef AGB_WITH_TC
@@ -64,6 +65,8 @@ extern "C" int agb_damsm_fwd(const float* img, const float* words, int64_t ws_b,
                              float* att_out, const float* cnn, const float* rnn, float* scos_out,
                              void* workspace, size_t workspace_bytes, int math, void* stream) {
   if (!img || !words || !cap_lens || !m_out || !workspace) return fail_arg("null pointer");
+  const int save = math & AGB_MATH_SAVE;
+  math &= ~AGB_MATH_SAVE;
   if ((cnn != nullptr) != (rnn != nullptr) || (cnn != nullptr) != (scos_out != nullptr))
     return fail_arg("cnn, rnn and scos_out must be given together");
   if (!agb_damsm_supported(T, D, R, math)) return fail_unsupported("T=%d D=%d R=%d math=%d is outside the compiled range", T, D, R, math);
@@ -77,7 +80,7 @@ extern "C" int agb_damsm_fwd(const float* img, const float* words, int64_t ws_b,
   }
 #ifdef AGB_WITH_TC
   return damsm_tc_fwd(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, D, R, gamma1, gamma2, eps, row_offset,
-                      m_out, att_out, cnn, rnn, scos_out, workspace, workspace_bytes, math, st);
+                      m_out, att_out, cnn, rnn, scos_out, workspace, workspace_bytes, math, save, st);
 #else
   return fail_unsupported("library built without the tcgen05 kernels");
 #endif

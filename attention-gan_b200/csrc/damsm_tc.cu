@@ -231,6 +231,10 @@ struct FwdParams {
   float* m_out;
   int Bi, Bc, T, R;
   float scale_log2, g1_log2, gamma2;
+  // training forward (kSave) / streaming backward: saved per (image, word row), Ntot = nt_max * 128 rows per image
+  void* v16;             // [Bi, Ntot, 256] 16-bit normalised context vectors
+  float4* rowst;         // [Bi, Ntot] {<w,v>, |v|, 1/Z, -}
+  int Ntot;
 };
 
 #include "damsm_tc_fwd2.inc"
@@ -245,7 +249,20 @@ struct TcPlan {
   int ct;        // tiles per chunk
   int splits;    // slices of the image range in the d words GEMM
   size_t off_E16, off_dV16, off_A116, off_dpp, off_dwp, off_m, total;
+  // what the training forward saves for the streaming backward (damsm_bwd3_kernel); save == 0: the saved
+  // context vectors would not fit the budget (or AGB_DAMSM_BWD=2) and the backward recomputes (damsm_bwd2_kernel)
+  int save;
+  size_t off_v16, off_rowst;
 };
+
+static bool force_bwd2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_DAMSM_BWD");
+    v = (e && e[0] == '2') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   TcPlan p;
@@ -276,6 +293,13 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_dpp = take(rows * 4);
   p.off_dwp = take((size_t)p.splits * ct * kTileN * kD * 4);
   p.off_m = take((size_t)Bi * Bc * 4);
+  const size_t all_rows = (size_t)Bi * p.nt_max * kTileN;
+  p.save = (all_rows * (kD * 2 + 16) <= ((size_t)64 << 30) && !force_bwd2()) ? 1 : 0;
+  p.off_v16 = p.off_rowst = o;
+  if (p.save) {
+    p.off_v16 = take(all_rows * kD * 2);
+    p.off_rowst = take(all_rows * 16);
+  }
   p.total = o;
   return p;
 }
@@ -325,20 +349,21 @@ static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t 
 
 template <typename T16>
 static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1,
-                      float gamma2, float* m_out, const TcPlan& pl, cudaStream_t st);
+                      float gamma2, float* m_out, char* ws, const TcPlan& pl, bool save, cudaStream_t st);
 
 template <typename T16>
 static int run_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                    const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1, float gamma2, float* m_out,
-                   char* ws, const TcPlan& pl, cudaStream_t st) {
+                   char* ws, const TcPlan& pl, bool save, cudaStream_t st) {
   Packed pk;
   if (int rc = run_pack<T16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, ws, pl, &pk, st)) return rc;
-  return launch_fwd<T16>(pk, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, pl, st);
+  return launch_fwd<T16>(pk, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save, st);
 }
 
 template <typename T16>
 static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc, int T, int R, float gamma1,
-                      float gamma2, float* m_out, const TcPlan& pl, cudaStream_t st) {
+                      float gamma2, float* m_out, char* ws, const TcPlan& pl, bool save, cudaStream_t st) {
+  save = save && pl.save;
   const bool bf = std::is_same<T16, __nv_bfloat16>::value;
   CUtensorMap mapW, mapCt, mapCk;
   if (int rc = make_tmap_2d(&mapW, pk.Wh, (uint64_t)pl.nt_max * kTileN, kD, 128, bf)) return rc;
@@ -350,7 +375,8 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
   p.scale_log2 = kLog2e / sqrtf((float)kD);
   p.g1_log2 = gamma1 * kLog2e;
   p.gamma2 = gamma2;
-  auto kern = damsm_fwd2_kernel<T16>;
+  p.v16 = ws + pl.off_v16; p.rowst = (float4*)(ws + pl.off_rowst); p.Ntot = pl.nt_max * kTileN;
+  auto kern = save ? damsm_fwd2_kernel<T16, true> : damsm_fwd2_kernel<T16, false>;
   AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
   const long long max_items = (long long)Bi * pl.nt_max;
   const int grid = (int)std::min<long long>(num_sms(), max_items);
@@ -361,6 +387,7 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
 }
 
 #include "damsm_tc_bwd2.inc"
+#include "damsm_tc_bwd3.inc"
 #include "damsm_tc_bwd2_host.inc"
 
 }  // namespace tc
@@ -372,7 +399,7 @@ size_t damsm_tc_workspace_bytes(int Bi, int Bc, int T, int D, int R) { return tc
 int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
                  float eps, int row_offset, float* m_out, float* att_out, const float* cnn, const float* rnn,
-                 float* scos_out, void* workspace, size_t workspace_bytes, int math, cudaStream_t st) {
+                 float* scos_out, void* workspace, size_t workspace_bytes, int math, int save, cudaStream_t st) {
   if (Bi <= 0 || Bc <= 0) return fail_arg("non-positive batch");
   if (Bi > 65535) return fail_unsupported("Bi=%d > 65535", Bi);
   if (math == AGB_MATH_TC_F16 && gamma1 > 11.f) return fail_unsupported("gamma1=%g overflows fp16 (use bf16 or fp32 math)", gamma1);
@@ -384,9 +411,9 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
   char* ws = (char*)workspace;
   int rc;
   if (math == AGB_MATH_TC_BF16)
-    rc = tc::run_fwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, st);
+    rc = tc::run_fwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
   else
-    rc = tc::run_fwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, st);
+    rc = tc::run_fwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
   if (rc) return rc;
   if (att_out) {
     if (row_offset < 0 || row_offset + Bi > Bc) return fail_arg("row_offset=%d out of range", row_offset);
@@ -408,6 +435,13 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
   if (workspace_bytes < pl.total) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
     return AGB_E_WORKSPACE;
+  }
+  if (pl.save) {
+    if (math == AGB_MATH_TC_BF16)
+      return tc::run_bwd3<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd,
+                                         gscale, dimg, dwords, (char*)workspace, pl, ws_from_fwd, st);
+    return tc::run_bwd3<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd, gscale,
+                                dimg, dwords, (char*)workspace, pl, ws_from_fwd, st);
   }
   if (math == AGB_MATH_TC_BF16)
     return tc::run_bwd2<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, dm, m_fwd,

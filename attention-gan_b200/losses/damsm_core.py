@@ -115,9 +115,13 @@ class _WordsLossFn(torch.autograd.Function):
             rnn32 = rnn.detach().float().reshape(rnn.shape[-2], -1).contiguous()
             if ex.W > 1:
                 rnn32 = _gather_cat(rnn32, cfg.group)
+        save = cfg.math != native.AGB_MATH_FP32 and any(ctx.needs_input_grad[:2])   # training forward
         m, att, scos, ws = o.damsm_fwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, ex.row0, cfg.want_att,
-                                       cfg.math, cnn32 if fuse_sent else None, rnn32 if fuse_sent else None, True)
-        ctx.ws = ws if cfg.math != native.AGB_MATH_FP32 else None    # packed 16-bit operands, reused by backward
+                                       cfg.math, cnn32 if fuse_sent else None, rnn32 if fuse_sent else None, True,
+                                       save)
+        # packed 16-bit operands (and, after a training forward, the saved context vectors), reused by backward
+        ctx.ws = ws if cfg.math != native.AGB_MATH_FP32 else None
+        ctx.ws_saved = save
         m_all = _gather_cat(m, cfg.group) if ex.W > 1 else m
         loss, dm = o.contrastive(m_all, ex.cls, ex.labels, cfg.gamma3, cfg.lam, ex.row0, Bl)
         ctx.save_for_backward(img3, w32, dm, m)
@@ -142,7 +146,7 @@ class _WordsLossFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[1]
         gscale = dloss.detach().float().reshape(1).contiguous()
         dimg, dwords = cfg.ops.damsm_bwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, dm, gscale, need_w,
-                                         cfg.math, m, ctx.ws)
+                                         cfg.math, m, ctx.ws, ctx.ws_saved)
         ctx.ws = None
         if dwords is not None:
             if ex.W > 1:

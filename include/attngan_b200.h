@@ -36,7 +36,12 @@ enum agb_dtype { AGB_F32 = 0, AGB_BF16 = 1, AGB_F16 = 2 };
 enum agb_math {
   AGB_MATH_FP32 = 0,    /* CUDA-core fp32 (bit-for-bit deterministic forward, 1e-6 parity)      */
   AGB_MATH_TC_F16 = 1,  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM (default)   */
-  AGB_MATH_TC_BF16 = 2  /* tcgen05 kind::f16, bf16 operands                                      */
+  AGB_MATH_TC_BF16 = 2, /* tcgen05 kind::f16, bf16 operands                                      */
+  /* flag, OR-ed into `math` of agb_damsm_fwd by a caller that will run agb_damsm_bwd on the same
+   * workspace (ws_from_fwd = 2): the tensor-core forward then also saves the normalised context
+   * vectors and their statistics in the workspace and the backward does not recompute them.
+   * Ignored by the fp32 path. */
+  AGB_MATH_SAVE = 0x100
 };
 
 enum agb_status {
@@ -142,6 +147,7 @@ int agb_damsm_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws
  *                    path recomputes it; the fp32 path does not need it)
  *   ws_from_fwd      != 0: `workspace` is the untouched buffer the matching agb_damsm_fwd call (same
  *                    inputs, same math) used; the tensor-core path then reuses its packed operands
+ *                    (1) and, if that call had AGB_MATH_SAVE set, its saved context vectors (2)
  *   gscale  device scalar (upstream d/dloss) or NULL for 1
  *   dimg    [Bi,D,R] fp32 out (overwritten)
  *   dwords  [Bc,T,D] fp32 contiguous out (note: word-major, the RNN's physical layout), or NULL

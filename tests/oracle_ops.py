@@ -16,7 +16,7 @@ def _np(t):
 
 
 def damsm_fwd(img, words, cap_lens, gamma1, gamma2, eps=1e-8, row_offset=0, want_att=True, math=0,
-              cnn=None, rnn=None, keep_ws=False):
+              cnn=None, rnn=None, keep_ws=False, save=False):
     c, w, lens = _np(img).astype(np.float64), _np(words).astype(np.float64), _np(cap_lens)
     m = cf.words_similarity_fwd(c, w, lens, gamma1, gamma2, eps)
     att = None
@@ -37,7 +37,8 @@ def damsm_fwd(img, words, cap_lens, gamma1, gamma2, eps=1e-8, row_offset=0, want
     return torch.from_numpy(m).float(), att, scos
 
 
-def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords, math=0, m_fwd=None, ws=None):
+def damsm_bwd(img, words, cap_lens, gamma1, gamma2, eps, dm, gscale, need_dwords, math=0, m_fwd=None, ws=None,
+              ws_saved=False):
     g = 1.0 if gscale is None else float(gscale.item())
     dc, dw = cf.words_similarity_bwd(_np(img), _np(words), _np(cap_lens), _np(dm).astype(np.float64) * g,
                                      gamma1, gamma2, eps)

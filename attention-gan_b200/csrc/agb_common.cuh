@@ -136,6 +136,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for single-thread roles (TMA producer, MMA issuer) whose waits are long: back off between polls so the
+// spin does not compete with the working warps of the same scheduler for issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
 // global -> shared bulk copy through the TMA unit (SASS: UBLKCP); bytes % 16 == 0, both 16B aligned
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                             uint64_t* bar) {

@@ -410,19 +410,28 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
   }
   char* ws = (char*)workspace;
   int rc;
+  // the matched-pair attention maps and the sentence cosine only read the caller's inputs: they run on a
+  // forked stream beside the pack kernels and the pair kernel and join before this call returns
+  tc::SideStream* side = nullptr;
+  if (att_out || cnn) {
+    if (att_out && (row_offset < 0 || row_offset + Bi > Bc)) return fail_arg("row_offset=%d out of range", row_offset);
+    if ((rc = tc::side_stream(&side))) return rc;
+    AGB_CUDA(cudaEventRecord(side->fork, st));
+    AGB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    if (att_out) {
+      rc = damsm_diag_att_maps(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, T, D, R, gamma1, row_offset, att_out,
+                               (float*)(ws + pl.off_attS), (float*)(ws + pl.off_attB), side->stream);
+      if (rc) return rc;
+    }
+    if (cnn && (rc = sent_cos_fwd_launch(cnn, rnn, Bi, Bc, D, eps, scos_out, side->stream))) return rc;
+    AGB_CUDA(cudaEventRecord(side->join, side->stream));
+  }
   if (math == AGB_MATH_TC_BF16)
     rc = tc::run_fwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
   else
     rc = tc::run_fwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
-  if (rc) return rc;
-  if (att_out) {
-    if (row_offset < 0 || row_offset + Bi > Bc) return fail_arg("row_offset=%d out of range", row_offset);
-    rc = damsm_diag_att_maps(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, T, D, R, gamma1, row_offset, att_out,
-                             (float*)(ws + pl.off_attS), (float*)(ws + pl.off_attB), st);
-    if (rc) return rc;
-  }
-  if (cnn) return sent_cos_fwd_launch(cnn, rnn, Bi, Bc, D, eps, scos_out, st);
-  return 0;
+  if (side) AGB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  return rc;
 }
 
 int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,

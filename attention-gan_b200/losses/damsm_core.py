@@ -221,6 +221,31 @@ def damsm_losses(img_features, cnn_code, words_emb, rnn_code, labels, cap_lens, 
     Returns (wloss, sloss, packed att or None)."""
     wcfg.ops.require_cuda(img_features, words_emb, cnn_code, rnn_code) if hasattr(wcfg.ops, "require_cuda") else None
     ex = _Exchange(wcfg, img_features.shape[0], labels, cap_lens, class_ids, img_features.device)
+    if ex.W == 1 and img_features.is_cuda:
+        # Single process: the sentence loss (cosine matrix, its contrastive CE and, in backward, its two
+        # gradient kernels) is independent of the word-region kernels, so it runs on a forked stream beside
+        # them.  Autograd replays each node's backward on its forward stream, so the overlap carries over
+        # to the backward pass; the fork / join are events, i.e. capturable in a CUDA graph.
+        main = torch.cuda.current_stream(img_features.device)
+        side = _side_stream(img_features.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            sloss = _SentLossFn.apply(cnn_code, rnn_code, scfg, ex, None)
+        wloss, att = _WordsLossFn.apply(img_features, words_emb, wcfg, ex, None, None)
+        main.wait_stream(side)
+        sloss.record_stream(main)
+        return wloss, sloss, (att if wcfg.want_att else None)
     wloss, att, scos = _WordsLossFn.apply(img_features, words_emb, wcfg, ex, cnn_code, rnn_code)
     sloss = _SentLossFn.apply(cnn_code, rnn_code, scfg, ex, scos)
     return wloss, sloss, (att if wcfg.want_att else None)
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return s

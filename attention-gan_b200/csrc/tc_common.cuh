@@ -28,7 +28,7 @@ constexpr int kChunkBytes16 = 128 * 128;   // one [128 x 64] 16-bit swizzled til
 struct TcGemmArgs {
   int a_mn, b_mn;              // 0: K-major array (rows = m|n, cols = k), 1: MN-major (rows = k, cols = m|n)
   int bf16;                    // operand type: 0 = fp16, 1 = bf16
-  int M, N, K, KB, NT;         // K % 64 == 0; NT = 64 or 128 output columns per CTA
+  int M, N, K, KB, NT;         // K % 64 == 0; NT = 64, 128, 192 or 256 output columns per CTA (MT * NT <= 512)
   int64_t a_zrow, a_zcol, a_kbrow, a_kbcol;   // offsets into map A per batch z / reduction block kb
   int64_t b_zrow, b_zcol, b_kbrow, b_kbcol;
   float* C;
@@ -47,6 +47,7 @@ struct TcGemmArgs {
   int nsrc;                    // 1, or 2: a second (A2, B2) operand pair continues the same reduction
   int64_t a2_zrow, b2_zrow;    // batch row offsets of the second pair
   int64_t a2_zcol, b2_zcol;    // batch column offsets of the second pair
+  int NT0;                     // != 0 (MN-major B only): CTA column 0 covers NT0 output columns, the others NT each
 };
 int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st);
 int tc_gemm2(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapA2,

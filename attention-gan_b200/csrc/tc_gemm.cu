@@ -2,7 +2,7 @@
 //
 //   C[z][m, n] (+)= alpha * sum_{kb < KB} sum_{k < K} A[z][kb][m, k] * B[z][kb][n, k]
 //
-// One CTA per 128 x NT output tile (NT = 64 or 128).  Operands are read by TMA through 2-D tensor
+// One CTA per (128 * MT) x NT output tile (NT = 64 ... 256, MT * NT <= 512 TMEM columns).  Operands are read by TMA through 2-D tensor
 // maps laid over the whole operand arrays; each operand is either K-major (array rows = m or n,
 // columns = k) or MN-major (array rows = k, columns = m or n), so the transposes that the DAMSM
 // backward needs (d img = dV^T beta, ...) cost nothing.  (z, kb) select sub-matrices through
@@ -43,7 +43,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int MT = g.MT;                                  // 128-row tiles per CTA sharing the B operand
-  const int n0 = blockIdx.x * g.NT, m0 = blockIdx.y * 128 * MT, z = blockIdx.z;
+  // output columns of this CTA: NT each, except that column 0 may be wider / narrower (NT0)
+  const int NT = (g.NT0 && blockIdx.x == 0) ? g.NT0 : g.NT;
+  const int n0 = g.NT0 ? (blockIdx.x == 0 ? 0 : g.NT0 + ((int)blockIdx.x - 1) * g.NT) : (int)blockIdx.x * g.NT;
+  const int m0 = blockIdx.y * 128 * MT, z = blockIdx.z;
   int kchunks = g.K >> 6;
   int kb_begin = 0, kb_count = g.KB;
   const int zb = g.split_kb ? 0 : z;                   // batch index used for operand offsets
@@ -62,8 +65,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int total = g.nsrc * per_src;
   if (total == 0 && g.accumulate) return;              // empty reduction added to C: nothing to do
   const int stages = g.stages;
-  const int stage_bytes = MT * kChunkBytes16 + g.NT * 128;
-  const uint32_t tmem_cols = MT * g.NT <= 128 ? 128u : 256u;
+  const int stage_bytes = MT * kChunkBytes16 + NT * 128;
+  const uint32_t tmem_cols = MT * NT <= 128 ? 128u : (MT * NT <= 256 ? 256u : 512u);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
@@ -110,14 +113,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (!g.b_mn) {
           tma_load_2d(sb, mB, &full[s], bcol + k0, brow + n0);                    // [NT n][64 k]
         } else {
-          for (int nb = 0; nb < g.NT / 64; ++nb)
+          for (int nb = 0; nb < NT / 64; ++nb)
             tma_load_2d(sb + nb * 8192, mB, &full[s], bcol + n0 + nb * 64, brow + k0);
         }
       }
     }
   } else if (warp == 5) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(128, g.NT, g.bf16) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16);
+      const uint32_t idesc = make_idesc(128, NT, g.bf16) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16);
       for (int it = 0; it < total; ++it) {
         const int s = it % stages, use = it / stages;
         mbar_wait(&full[s], use & 1);
@@ -129,7 +132,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int mt = 0; mt < MT; ++mt) {
             const uint32_t sam = sa + mt * kChunkBytes16;
             const uint64_t da = g.a_mn ? make_desc_sw128_mn(sam + kk * 2048, 8192) : make_desc_sw128(sam) + 2 * kk;
-            umma_f16(tmem + mt * g.NT, da, db, idesc, (it | kk) ? 1u : 0u);
+            umma_f16(tmem + mt * NT, da, db, idesc, (it | kk) ? 1u : 0u);
           }
         }
         umma_commit(&empty[s]);
@@ -149,13 +152,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // n-contiguous output: transpose through shared memory (the operand ring is idle now) so that
         // every warp writes whole rows -- coalesced for any row pitch / alignment
         float* tile = reinterpret_cast<float*>(smem);          // [128][NT + 1]
-        const int pitch = g.NT + 1;
+        const int pitch = NT + 1;
         const int row = warp * 32 + lane;
         if (mt > 0) named_bar_sync(1, 128);                    // previous tile fully written out
-        for (int c0 = 0; c0 < g.NT; c0 += 32) {
+        for (int c0 = 0; c0 < NT; c0 += 32) {
           float v[32];
           if (total > 0) {
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * g.NT + c0, v);
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * NT + c0, v);
             tmem_ld_wait();
           } else {
 #pragma unroll
@@ -166,7 +169,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         named_bar_sync(1, 128);
         const int rows = min(128, m_valid - mbase);
-        const int cols = min(g.NT, g.N - n0);
+        const int cols = min(NT, g.N - n0);
         for (int r = warp; r < rows; r += 4) {
           float* prow = Cz + (int64_t)(mbase + r) * g.c_m + n0;
           for (int n = lane; n < cols; n += 32) {
@@ -176,10 +179,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       } else {
         const int m = mbase + warp * 32 + lane;
-        for (int c0 = 0; c0 < g.NT; c0 += 32) {
+        for (int c0 = 0; c0 < NT; c0 += 32) {
           float v[32];
           if (total > 0) {
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * g.NT + c0, v);
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * NT + c0, v);
             tmem_ld_wait();
           } else {
 #pragma unroll
@@ -210,23 +213,26 @@ int tc_gemm2(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap&
   TcGemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
   if (g.K <= 0 || g.K % 64 || g.KB <= 0) return fail_arg("tc_gemm: K=%d must be a positive multiple of 64", g.K);
-  if (g.NT != 64 && g.NT != 128) return fail_arg("tc_gemm: NT=%d", g.NT);
+  if (g.NT != 64 && g.NT != 128 && g.NT != 192 && g.NT != 256) return fail_arg("tc_gemm: NT=%d", g.NT);
+  if (g.NT0 && (g.NT0 % 64 || g.NT0 > 256 || !g.b_mn)) return fail_arg("tc_gemm: NT0=%d", g.NT0);
   if (g.MT != 1 && g.MT != 2) g.MT = 1;
+  const int nt_max = std::max(g.NT, g.NT0);
+  if (g.MT * nt_max > 512) return fail_arg("tc_gemm: MT*NT=%d exceeds TMEM", g.MT * nt_max);
   if (g.nsrc != 2) g.nsrc = 1;
   static bool attr_set = false;
   if (!attr_set) {
     AGB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     attr_set = true;
   }
-  dim3 grid(cdiv(g.N, g.NT), cdiv(g.M, 128 * g.MT), batch);
+  dim3 grid(g.NT0 ? 1 + cdiv(std::max(0, g.N - g.NT0), g.NT) : cdiv(g.N, g.NT), cdiv(g.M, 128 * g.MT), batch);
   if (grid.y > 65535 || grid.z > 65535) return fail_unsupported("tc_gemm grid too large");
   // ring depth: as deep as ~192 KB allows; short reductions get a short ring so that several CTAs
   // share an SM and hide each other's prologue
-  const int stage_bytes = g.MT * kChunkBytes16 + g.NT * 128;
+  const int stage_bytes = g.MT * kChunkBytes16 + nt_max * 128;
   const long long chunks = (long long)g.nsrc * g.KB * (g.K / 64);
   const int max_stages = std::min(kGemmStages, (kGemmSmem - 1024) / stage_bytes);
   g.stages = (int)std::min<long long>(max_stages, std::max<long long>(2, chunks));
-  const int smem_bytes = std::max(g.stages * stage_bytes, 128 * (g.NT + 1) * 4) + 1024;
+  const int smem_bytes = std::max(g.stages * stage_bytes, 128 * (nt_max + 1) * 4) + 1024;
   const int slot = prof_begin(PROF_DAMSM_TC_BWD, st);
   tc_gemm_kernel<<<grid, 192, smem_bytes, st>>>(mapA, mapB, mapA2, mapB2, g);
   prof_end(slot, st);
@@ -245,17 +251,22 @@ int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& map
 using namespace agb;
 
 // Test hook: C[M,N] = A * B^T for one batch.  A is [M,K] row-major (a_mn = 0) or [K,M] (a_mn = 1);
-// B likewise with N.  M, N arbitrary (<= one grid), K % 64 == 0.
+// B likewise with N.  M, N arbitrary (<= one grid), K % 64 == 0.  `accumulate`: bit 0 = add to C; bits 8-15 /
+// 16-23 / 24-31 select the tiling under test: NT / 64 (0 = default), NT0 / 64, MT.
 extern "C" int agb_tc_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mn, int b_mn,
                                 int bf16, int accumulate, void* stream) {
   if (!A || !B || !C) return fail_arg("null pointer");
   CUtensorMap mapA, mapB;
-  const int NT = (N % 128 == 0 || N > 64) ? 128 : 64;
+  const int nt_sel = ((accumulate >> 8) & 0xff) * 64, nt0_sel = ((accumulate >> 16) & 0xff) * 64;
+  const int mt_sel = (accumulate >> 24) & 0xff;
+  accumulate &= 1;
+  const int NT = nt_sel ? nt_sel : ((N % 128 == 0 || N > 64) ? 128 : 64);
   // box rows: K-major operands load [128 or NT rows x 64]; MN-major operands load [64 k rows x 64]
   if (int rc = tc::make_tmap_2d(&mapA, A, a_mn ? K : M, a_mn ? M : K, a_mn ? 64 : 128, bf16 != 0)) return rc;
   if (int rc = tc::make_tmap_2d(&mapB, B, b_mn ? K : N, b_mn ? N : K, b_mn ? 64 : NT, bf16 != 0)) return rc;
   tc::TcGemmArgs g{};
   g.a_mn = a_mn; g.b_mn = b_mn; g.bf16 = bf16 ? 1 : 0; g.M = M; g.N = N; g.K = K; g.KB = 1; g.NT = NT;
   g.C = C; g.c_z = 0; g.c_m = N; g.c_n = 1; g.alpha = 1.f; g.accumulate = accumulate;
+  g.NT0 = nt0_sel; g.MT = mt_sel ? mt_sel : 1;
   return tc::tc_gemm(g, mapA, mapB, 1, (cudaStream_t)stream);
 }

@@ -55,6 +55,29 @@ def test_tc_gemm_all_majors(agb, a_mn, b_mn, M, N, K, bf16):
     assert err < 1e-5, f"rel err {err:.3e}"
 
 
+@pytest.mark.parametrize("a_mn,b_mn,NT,NT0,MT", [(0, 0, 256, 0, 2), (1, 0, 256, 0, 2), (1, 1, 128, 192, 2),
+                                                 (0, 1, 128, 192, 1), (1, 1, 192, 0, 2), (0, 0, 256, 0, 1)])
+@pytest.mark.parametrize("M,N,K", [(256, 296, 256), (296, 256, 192), (136, 520, 128)])
+def test_tc_gemm_wide_tiles(agb, a_mn, b_mn, NT, NT0, MT, M, N, K):
+    """the wide tilings of the DAMSM reductions: 256-column tiles (d words), a 192 + 128 column split (d img)"""
+    g = torch.Generator().manual_seed(M + N + K + NT)
+    A = torch.randn(M, K, generator=g).half()
+    B = torch.randn(N, K, generator=g).half()
+    Ad = (A.t().contiguous() if a_mn else A).cuda()
+    Bd = (B.t().contiguous() if b_mn else B).cuda()
+    C0 = torch.randn(M, N, generator=g)
+    C = C0.clone().cuda()
+    lib = agb.native.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    sel = 1 | ((NT // 64) << 8) | ((NT0 // 64) << 16) | (MT << 24)
+    agb.native.check(lib.agb_tc_gemm_test(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, a_mn, b_mn, 0, sel, st),
+                     "agb_tc_gemm_test")
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double() @ B.double().T
+    err = (C.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, f"rel err {err:.3e}"
+
+
 # ------------------------------------------------------------------------------------------------
 # fused tcgen05 DAMSM kernels (AGB_MATH_TC_F16 / _BF16) against the oracle
 # ------------------------------------------------------------------------------------------------

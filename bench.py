@@ -443,7 +443,7 @@ def run_native(args):
         peak = peaks["tf_burst"]
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": load_traffic(args.workload) if (tc and args.batch is None) else None,
-                "kernel": "damsm_fwd2_kernel + damsm_bwd2_kernel + tc_gemm_kernel (tcgen05)" if tc else "sgemm_strided_kernel (fp32 CUDA cores)",
+                "kernel": "damsm_fwd2_kernel + damsm_bwd3_kernel + tc_gemm_kernel (tcgen05)" if tc else "sgemm_strided_kernel (fp32 CUDA cores)",
                 "launches": int(n_l), "avg_launch_ms": ms_tot / max(n_l, 1),
                 "peak_source": f"{peaks['source']} bf16 burst (kernels timed one by one with events)",
                 "algorithmic": "12*R*mean(cap_len)*D flop per (image,caption) pair, fwd+bwd"}

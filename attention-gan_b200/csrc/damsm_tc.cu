@@ -47,6 +47,9 @@ constexpr int kRRows = 384;               // region rows per image in Ct (3 M-ti
 constexpr int kRCols = 320;               // region columns per image in Ck / e (5 chunks of 64)
 constexpr int kChunk = 128 * 128;         // one [128 x 64] 16-bit K-major tile: 16 KB
 constexpr int kSlot = 2 * kChunk;         // ring slot: 32 KB
+// per-item cost model of the pair kernels, in units of one caption word slot (fitted to per-CTA times of the
+// streaming backward, scripts/bwd3_timeline.py): fixed part per (word tile, image) item and per caption
+constexpr int kItemCost0 = 900, kItemCostCap = 32;
 constexpr int kThreads = 448;             // warps 0-11 epilogue, 12 TMA producer (+ TMEM alloc), 13 MMA issuer
 constexpr int kSmemW = 0;                 // [4][128 x 64]  resident word tile       64 KB
 constexpr int kSmemE = 4 * kChunk;        // [5][128 x 64]  e = exp(gamma1 alpha)    80 KB
@@ -68,11 +71,13 @@ template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u)
 // pack kernels
 // ---------------------------------------------------------------------------------------------
 // greedy packing of whole captions into tiles of <= 128 word rows (and <= 128 captions)
+// tile_cpre[t] = exclusive prefix of the per-item cost estimate of word tile t (see cta_items_balanced)
 __global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, int T, int32_t* __restrict__ cap_row,
                                  int32_t* __restrict__ tile_first, int32_t* __restrict__ tile_ncap,
-                                 int32_t* __restrict__ ntiles) {
+                                 int32_t* __restrict__ ntiles, int32_t* __restrict__ tile_cpre) {
   __shared__ int lens_s[1024];
   int row = 0, tile = 0, first = 0;
+  int cost = kItemCost0, cpre = 0;
   for (int base = 0; base < Bc; base += 1024) {
     const int n = min(1024, Bc - base);
     __syncthreads();
@@ -86,18 +91,24 @@ __global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, i
         if (row + ((L + 3) & ~3) > kTileN || i - first == 128) {
           tile_first[tile] = first;
           tile_ncap[tile] = i - first;
+          tile_cpre[tile] = cpre;
+          cpre += cost;
+          cost = kItemCost0;
           ++tile;
           first = i;
           row = 0;
         }
         cap_row[i] = tile * kTileN + row;
         row += L;
+        if (L > 0) cost += ((L + 3) & ~3) + kItemCostCap;
       }
     }
   }
   if (threadIdx.x == 0) {
     tile_first[tile] = first;
     tile_ncap[tile] = Bc - first;
+    tile_cpre[tile] = cpre;
+    tile_cpre[tile + 1] = cpre + cost;
     ntiles[0] = tile + 1;
   }
 }
@@ -227,6 +238,8 @@ struct FwdParams {
   const int32_t* ntiles;
   const int32_t* cap_row;
   const int32_t* cap_lens;
+  const int32_t* tile_cpre;   // [ntiles + 1] exclusive prefix of the per-item cost of each word tile
+  int uniform_split;          // != 0: equal item counts per CTA instead of equal cost (AGB_DAMSM_DEBUG & 32, for A/B timing)
   const float* pn;
   float* m_out;
   int Bi, Bc, T, R;
@@ -244,7 +257,7 @@ struct FwdParams {
 // ---------------------------------------------------------------------------------------------
 struct TcPlan {
   int nt_max;
-  size_t off_Wh, off_pn, off_caprow, off_tfirst, off_tncap, off_ntiles, off_Ct, off_Ck, off_attS, off_attB;
+  size_t off_Wh, off_pn, off_caprow, off_tfirst, off_tncap, off_tcpre, off_ntiles, off_Ct, off_Ck, off_attS, off_attB;
   // fused backward staging, per chunk of ct word tiles (N = ct*128 word rows) and all Bi images
   int ct;        // tiles per chunk
   int splits;    // slices of the image range in the d words GEMM
@@ -275,6 +288,7 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_caprow = take((size_t)Bc * 4);
   p.off_tfirst = take((size_t)p.nt_max * 4);
   p.off_tncap = take((size_t)p.nt_max * 4);
+  p.off_tcpre = take((size_t)(p.nt_max + 1) * 4);
   p.off_ntiles = take(256);
   p.off_Ct = take((size_t)Bi * kRRows * kD * 2);
   p.off_Ck = take((size_t)Bi * kD * kRCols * 2);
@@ -316,7 +330,7 @@ static int num_sms() {
 }
 
 struct Packed {
-  void* Wh; float* pn; int32_t *cap_row, *tfirst, *tncap, *ntiles; void* Ct; void* Ck;
+  void* Wh; float* pn; int32_t *cap_row, *tfirst, *tncap, *tcpre, *ntiles; void* Ct; void* Ck;
 };
 
 // pack the operands of one call: caption tiles, 16-bit words, 16-bit region features (both layouts)
@@ -329,20 +343,21 @@ static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t 
   int32_t* cap_row = (int32_t*)(ws + pl.off_caprow);
   int32_t* tfirst = (int32_t*)(ws + pl.off_tfirst);
   int32_t* tncap = (int32_t*)(ws + pl.off_tncap);
+  int32_t* tcpre = (int32_t*)(ws + pl.off_tcpre);
   int32_t* ntiles = (int32_t*)(ws + pl.off_ntiles);
   T16* Ct = (T16*)(ws + pl.off_Ct);
   T16* Ck = (T16*)(ws + pl.off_Ck);
   if (!already_packed) {
     AGB_CUDA(cudaMemsetAsync(Wh, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
     AGB_CUDA(cudaMemsetAsync(pn, 0, (size_t)pl.nt_max * kTileN * 4, st));
-    tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, cap_row, tfirst, tncap, ntiles);
+    tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, cap_row, tfirst, tncap, ntiles, tcpre);
     if (int rc = check_launch("tile_pack_kernel")) return rc;
     pack_words_kernel_tc<T16><<<dim3(Bc, T), 128, 0, st>>>(words, ws_b, ws_d, ws_t, cap_lens, cap_row, Wh, pn, T);
     if (int rc = check_launch("pack_words_kernel_tc")) return rc;
     pack_img_kernel_tc<T16><<<dim3(kRRows / 32, kD / 32, Bi), dim3(32, 8), 0, st>>>(img, Ck, Ct, R);
     if (int rc = check_launch("pack_img_kernel_tc")) return rc;
   }
-  out->Wh = Wh; out->pn = pn; out->cap_row = cap_row; out->tfirst = tfirst; out->tncap = tncap; out->ntiles = ntiles;
+  out->Wh = Wh; out->pn = pn; out->cap_row = cap_row; out->tfirst = tfirst; out->tncap = tncap; out->tcpre = tcpre; out->ntiles = ntiles;
   out->Ct = Ct; out->Ck = Ck;
   return 0;
 }
@@ -371,6 +386,8 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
   if (int rc = make_tmap_2d(&mapCk, pk.Ck, (uint64_t)Bi * kD, kRCols, 128, bf)) return rc;
   FwdParams p;
   p.tile_first = pk.tfirst; p.tile_ncap = pk.tncap; p.ntiles = pk.ntiles; p.cap_row = pk.cap_row; p.cap_lens = cap_lens;
+  p.tile_cpre = pk.tcpre;
+  { const char* e = getenv("AGB_DAMSM_DEBUG"); p.uniform_split = e ? (atoi(e) & 32) : 0; }
   p.pn = pk.pn; p.m_out = m_out; p.Bi = Bi; p.Bc = Bc; p.T = T; p.R = R;
   p.scale_log2 = kLog2e / sqrtf((float)kD);
   p.g1_log2 = gamma1 * kLog2e;
@@ -460,3 +477,13 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
 }
 
 }  // namespace agb
+
+// debug hook (not part of the public header): the timeline CTA 0 of damsm_bwd3_kernel recorded under AGB_DAMSM_DEBUG & 16
+extern "C" int agb_damsm_debug_timeline(long long* out, int n) {
+  const size_t bytes = std::min((size_t)n * 8, sizeof(agb::tc::g_tl));
+  return (int)cudaMemcpyFromSymbol(out, agb::tc::g_tl, bytes);
+}
+extern "C" int agb_damsm_debug_cta_times(long long* out, int n) {
+  const size_t bytes = std::min((size_t)n * 8, sizeof(agb::tc::g_tl_cta));
+  return (int)cudaMemcpyFromSymbol(out, agb::tc::g_tl_cta, bytes);
+}

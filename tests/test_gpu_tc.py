@@ -220,3 +220,29 @@ def test_tc_unsupported_shapes_fail_loudly(agb):
         ops.damsm_fwd(torch.zeros(2, 128, 289, device="cuda"), torch.zeros(2, 128, 18, device="cuda"),
                       torch.full((2,), 18, dtype=torch.int32, device="cuda"), 4.0, 5.0, 1e-8, 0, False,
                       native.AGB_MATH_TC_F16)
+
+
+def test_tc_recomputing_backward_fallback():
+    """AGB_DAMSM_BWD=2 selects the recomputing backward kernel (the path taken when the training forward's saved
+    context vectors would not fit); it is read once per process, so the check runs in a child process."""
+    import os, subprocess, sys
+    code = r'''
+import numpy as np, torch
+import attention_gan_b200 as agb
+from oracle import closed_form as cf
+from oracle import ref_port as rp
+B = 24
+img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, seed=3, n_classes=6)
+wl0, _, dc0, dw0 = cf.words_loss_fwd_bwd(img.numpy().reshape(B, 256, -1), wrd.numpy(), labels.numpy(), lens.numpy(), cls)
+im = img.cuda().requires_grad_(True); wd = wrd.cuda().requires_grad_(True)
+wl, _ = agb.WordsLoss("cuda", math="f16").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
+wl.backward()
+rel = lambda x, r: np.abs(x.detach().double().cpu().numpy() - r).max() / np.abs(r).max()
+assert abs(wl.item() - wl0) <= 1e-4 * abs(wl0), (wl.item(), wl0)
+assert rel(im.grad, dc0.reshape(img.shape)) < 5e-3 and rel(wd.grad, dw0) < 5e-3
+print("fallback ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AGB_DAMSM_BWD="2", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout + r.stderr

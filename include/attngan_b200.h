@@ -129,7 +129,8 @@ int agb_word_attn_bwd(const void* images, const float* words, int64_t ws_b, int6
  *                      rows t >= L zeroed (:63)
  *   cnn,rnn  [Bi,D],[Bc,D] fp32 contiguous or both NULL; when given, the raw cosine matrix
  *   scos_out [Bi,Bc]   of SentenceLoss (sentence_loss.py:33-38, before *gamma3) is produced by
- *                      extra thread blocks of the SAME launch
+ *                      the same call (its kernel runs on a forked stream beside the pair kernel
+ *                      and is joined back into `stream` before the call returns)
  *   row_offset         global index of local image 0 when the batch is sharded over ranks
  * Limits: D % 32 == 0, D <= 256 (tcgen05: D == 256... see agb_damsm_supported), T <= 64.
  * ---------------------------------------------------------------------------------------------- */

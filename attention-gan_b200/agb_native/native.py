@@ -25,6 +25,7 @@ SIGNATURES = {
     "agb_tc_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "agb_tc_gemm_test": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
+    "agb_set_option": (c_int, [c_char_p, ctypes.c_longlong]),
     "agb_launch_count": (ctypes.c_longlong, []),
     "agb_prof_enable": (None, [c_int]),
     "agb_prof_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
@@ -83,6 +84,11 @@ def lib() -> ctypes.CDLL:
 
 class NativeError(RuntimeError):
     pass
+
+
+def set_option(name: str, value: int) -> None:
+    """process-wide tuning / test option (include/attngan_b200.h: agb_set_option)"""
+    check(lib().agb_set_option(name.encode(), int(value)), f"agb_set_option({name})")
 
 
 def check(rc: int, what: str) -> None:

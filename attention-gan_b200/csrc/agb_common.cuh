@@ -17,9 +17,21 @@ int fail_unsupported(const char* fmt, ...);  // returns AGB_E_UNSUPPORTED
 int check_launch(const char* what);          // cudaGetLastError -> return code; counts the launch
 
 // optional per-kernel timing for bench.py (agb_prof_enable / agb_prof_read); no-ops when disabled
-enum ProfTag { PROF_SGEMM = 1, PROF_DAMSM_TC_FWD = 2, PROF_DAMSM_TC_BWD = 3, PROF_ATTN_FWD = 4, PROF_ATTN_BWD = 5 };
+enum ProfTag { PROF_SGEMM = 1, PROF_DAMSM_TC_FWD = 2, PROF_DAMSM_TC_BWD = 3, PROF_ATTN_FWD = 4, PROF_ATTN_BWD = 5,
+               PROF_DAMSM_DIMG = 6, PROF_DAMSM_DWORDS = 7, PROF_DAMSM_PACK = 8, PROF_MAX = 16 };
 int prof_begin(int tag, cudaStream_t st);
 void prof_end(int slot, cudaStream_t st);
+
+// ---- process-wide options: read from the environment ONCE (first use), or set through agb_set_option() ----
+struct Options {
+  long long damsm_chunk_bytes;   // staging budget of one backward chunk of word tiles   (AGB_DAMSM_CHUNK_MB)
+  long long damsm_save_bytes;    // budget of what the training forward saves            (AGB_DAMSM_SAVE_MB)
+  int damsm_bwd;                 // 2 = always the recomputing backward                  (AGB_DAMSM_BWD)
+  int damsm_uniform_split;       // != 0: equal item counts per CTA, not equal cost      (AGB_DAMSM_UNIFORM_SPLIT)
+  int attn_fwd_stages, attn_fwd_ctas, attn_bwd_stages, attn_bwd_ctas;   // tuning knobs  (AGB_ATTN_*), 0 = automatic
+};
+const Options& options();
+int device_sms();                // SM count of the current device (cached per device ordinal)
 
 #define AGB_CUDA(expr)                                                         \
   do {                                                                         \

@@ -1,8 +1,10 @@
 // Error plumbing and library identity for libattngan_b200 (C ABI in include/attngan_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "agb_common.cuh"
@@ -41,6 +43,39 @@ int check_launch(const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("%s: %s", what, cudaGetErrorString(e));
   return (int)e;
+}
+
+// ---- options ----------------------------------------------------------------------------------
+static Options g_opt;
+static std::once_flag g_opt_once;
+static long long env_ll(const char* name, long long dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoll(e) : dflt;
+}
+static void load_options() {
+  g_opt.damsm_chunk_bytes = env_ll("AGB_DAMSM_CHUNK_MB", 16384) << 20;
+  g_opt.damsm_save_bytes = env_ll("AGB_DAMSM_SAVE_MB", 65536) << 20;
+  g_opt.damsm_bwd = (int)env_ll("AGB_DAMSM_BWD", 0);
+  g_opt.damsm_uniform_split = (int)env_ll("AGB_DAMSM_UNIFORM_SPLIT", 0);
+  g_opt.attn_fwd_stages = (int)env_ll("AGB_ATTN_FWD_STAGES", 0);
+  g_opt.attn_fwd_ctas = (int)env_ll("AGB_ATTN_FWD_CTAS", 0);
+  g_opt.attn_bwd_stages = (int)env_ll("AGB_ATTN_BWD_STAGES", 0);
+  g_opt.attn_bwd_ctas = (int)env_ll("AGB_ATTN_BWD_CTAS", 0);
+}
+const Options& options() {
+  std::call_once(g_opt_once, load_options);
+  return g_opt;
+}
+int device_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
 }
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) -------------------------
@@ -104,6 +139,23 @@ extern "C" int agb_prof_read(int tag, double* total_ms, long long* launches) {
   if (total_ms) *total_ms = tot;
   if (launches) *launches = n;
   return agb::g_prof_dropped ? -3 : 0;
+}
+
+extern "C" int agb_set_option(const char* name, long long value) {
+  if (!name) return agb::fail_arg("null option name");
+  agb::options();   // environment first, then the override
+  const std::string n(name);
+  agb::Options& o = agb::g_opt;
+  if (n == "damsm_chunk_mb") o.damsm_chunk_bytes = value << 20;
+  else if (n == "damsm_save_mb") o.damsm_save_bytes = value << 20;
+  else if (n == "damsm_bwd") o.damsm_bwd = (int)value;
+  else if (n == "damsm_uniform_split") o.damsm_uniform_split = (int)value;
+  else if (n == "attn_fwd_stages") o.attn_fwd_stages = (int)value;
+  else if (n == "attn_fwd_ctas") o.attn_fwd_ctas = (int)value;
+  else if (n == "attn_bwd_stages") o.attn_bwd_stages = (int)value;
+  else if (n == "attn_bwd_ctas") o.attn_bwd_ctas = (int)value;
+  else return agb::fail_arg("unknown option '%s'", name);
+  return 0;
 }
 
 extern "C" long long agb_launch_count(void) { return agb::g_launches.load(); }

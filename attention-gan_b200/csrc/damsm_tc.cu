@@ -46,15 +46,12 @@ constexpr int kTileN = 128;               // word rows per tile
 constexpr int kRRows = 384;               // region rows per image in Ct (3 M-tiles)
 constexpr int kRCols = 320;               // region columns per image in Ck / e (5 chunks of 64)
 constexpr int kChunk = 128 * 128;         // one [128 x 64] 16-bit K-major tile: 16 KB
-constexpr int kSlot = 2 * kChunk;         // ring slot: 32 KB
 // per-item cost model of the pair kernels, in units of one caption word slot (fitted to per-CTA times of the
 // streaming backward, scripts/bwd3_timeline.py): fixed part per (word tile, image) item and per caption
 constexpr int kItemCost0 = 900, kItemCostCap = 32;
 constexpr int kThreads = 448;             // warps 0-11 epilogue, 12 TMA producer (+ TMEM alloc), 13 MMA issuer
 constexpr int kSmemW = 0;                 // [4][128 x 64]  resident word tile       64 KB
 constexpr int kSmemE = 4 * kChunk;        // [5][128 x 64]  e = exp(gamma1 alpha)    80 KB
-constexpr int kSmemRing = 9 * kChunk;     // 2 slots                                  64 KB
-constexpr int kSmemBytes = 13 * kChunk + 1024;
 
 template <typename T16> __device__ __forceinline__ T16 cvt16(float v);
 template <> __device__ __forceinline__ __half cvt16<__half>(float v) { return __float2half_rn(v); }
@@ -239,7 +236,7 @@ struct FwdParams {
   const int32_t* cap_row;
   const int32_t* cap_lens;
   const int32_t* tile_cpre;   // [ntiles + 1] exclusive prefix of the per-item cost of each word tile
-  int uniform_split;          // != 0: equal item counts per CTA instead of equal cost (AGB_DAMSM_DEBUG & 32, for A/B timing)
+  int uniform_split;          // != 0: equal item counts per CTA instead of equal cost (option damsm_uniform_split, for A/B timing)
   const float* pn;
   float* m_out;
   int Bi, Bc, T, R;
@@ -268,16 +265,8 @@ struct TcPlan {
   size_t off_v16, off_rowst;
 };
 
-static bool force_bwd2() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("AGB_DAMSM_BWD");
-    v = (e && e[0] == '2') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
+  const Options& opt = options();
   TcPlan p;
   const int per_tile = 128 / ((T + 3) & ~3);  // captions that always fit in one tile (4-column windows)
   p.nt_max = (Bc + per_tile - 1) / per_tile;
@@ -294,21 +283,22 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_Ck = take((size_t)Bi * kD * kRCols * 2);
   p.off_attS = take((size_t)Bi * T * R * 4);
   p.off_attB = take((size_t)Bi * T * R * 4);
-  const size_t tile_bytes = (size_t)Bi * kTileN * (kRCols * 2 * 2 + kD * 2 + 4);
-  size_t ct = ((size_t)8 << 30) / tile_bytes;
+  const size_t all_rows = (size_t)Bi * p.nt_max * kTileN;
+  p.save = (all_rows * (kD * 2 + 16) <= (size_t)std::max<long long>(0, opt.damsm_save_bytes) && opt.damsm_bwd != 2) ? 1 : 0;
+  // staging of one backward chunk: E16 + A116 (+ dV16 for the recomputing backward) + dpp per (image, word row)
+  const size_t tile_bytes = (size_t)Bi * kTileN * (kRCols * 2 * 2 + (p.save ? 0 : kD * 2) + 4);
+  size_t ct = (size_t)std::max<long long>(0, opt.damsm_chunk_bytes) / tile_bytes;
   if (ct < 1) ct = 1;
   if (ct > (size_t)p.nt_max) ct = p.nt_max;
   p.ct = (int)ct;
   p.splits = std::min(Bi, 16);
   const size_t rows = (size_t)Bi * ct * kTileN;
   p.off_E16 = take(rows * kRCols * 2);
-  p.off_dV16 = take(rows * kD * 2);
+  p.off_dV16 = p.save ? p.off_E16 : take(rows * kD * 2);
   p.off_A116 = take(rows * kRCols * 2);
   p.off_dpp = take(rows * 4);
   p.off_dwp = take((size_t)p.splits * ct * kTileN * kD * 4);
   p.off_m = take((size_t)Bi * Bc * 4);
-  const size_t all_rows = (size_t)Bi * p.nt_max * kTileN;
-  p.save = (all_rows * (kD * 2 + 16) <= ((size_t)64 << 30) && !force_bwd2()) ? 1 : 0;
   p.off_v16 = p.off_rowst = o;
   if (p.save) {
     p.off_v16 = take(all_rows * kD * 2);
@@ -318,16 +308,7 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   return p;
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+static int num_sms() { return device_sms(); }
 
 struct Packed {
   void* Wh; float* pn; int32_t *cap_row, *tfirst, *tncap, *tcpre, *ntiles; void* Ct; void* Ck;
@@ -387,7 +368,7 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
   FwdParams p;
   p.tile_first = pk.tfirst; p.tile_ncap = pk.tncap; p.ntiles = pk.ntiles; p.cap_row = pk.cap_row; p.cap_lens = cap_lens;
   p.tile_cpre = pk.tcpre;
-  { const char* e = getenv("AGB_DAMSM_DEBUG"); p.uniform_split = e ? (atoi(e) & 32) : 0; }
+  p.uniform_split = options().damsm_uniform_split;
   p.pn = pk.pn; p.m_out = m_out; p.Bi = Bi; p.Bc = Bc; p.T = T; p.R = R;
   p.scale_log2 = kLog2e / sqrtf((float)kD);
   p.g1_log2 = gamma1 * kLog2e;
@@ -430,24 +411,27 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
   // the matched-pair attention maps and the sentence cosine only read the caller's inputs: they run on a
   // forked stream beside the pack kernels and the pair kernel and join before this call returns
   tc::SideStream* side = nullptr;
+  int rc_side = 0;
   if (att_out || cnn) {
     if (att_out && (row_offset < 0 || row_offset + Bi > Bc)) return fail_arg("row_offset=%d out of range", row_offset);
     if ((rc = tc::side_stream(&side))) return rc;
-    AGB_CUDA(cudaEventRecord(side->fork, st));
-    AGB_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    if (att_out) {
-      rc = damsm_diag_att_maps(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, T, D, R, gamma1, row_offset, att_out,
-                               (float*)(ws + pl.off_attS), (float*)(ws + pl.off_attB), side->stream);
-      if (rc) return rc;
-    }
-    if (cnn && (rc = sent_cos_fwd_launch(cnn, rnn, Bi, Bc, D, eps, scos_out, side->stream))) return rc;
-    AGB_CUDA(cudaEventRecord(side->join, side->stream));
+    if ((rc = tc::side_fork(side, st))) return rc;
+    if (att_out)
+      rc_side = damsm_diag_att_maps(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, T, D, R, gamma1, row_offset, att_out,
+                                    (float*)(ws + pl.off_attS), (float*)(ws + pl.off_attB), side->stream);
+    if (cnn && rc_side == 0) rc_side = sent_cos_fwd_launch(cnn, rnn, Bi, Bc, D, eps, scos_out, side->stream);
   }
-  if (math == AGB_MATH_TC_BF16)
-    rc = tc::run_fwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
-  else
-    rc = tc::run_fwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
-  if (side) AGB_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+  if (rc_side == 0) {
+    if (math == AGB_MATH_TC_BF16)
+      rc = tc::run_fwd<__nv_bfloat16>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
+    else
+      rc = tc::run_fwd<__half>(img, words, ws_b, ws_d, ws_t, cap_lens, Bi, Bc, T, R, gamma1, gamma2, m_out, ws, pl, save != 0, st);
+  } else {
+    rc = rc_side;
+  }
+  // joined on every path after the fork (an enclosing graph capture must not be left forked)
+  if (side)
+    if (int rj = tc::side_join(side, st)) return rc ? rc : rj;
   return rc;
 }
 
@@ -478,7 +462,8 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
 
 }  // namespace agb
 
-// debug hook (not part of the public header): the timeline CTA 0 of damsm_bwd3_kernel recorded under AGB_DAMSM_DEBUG & 16
+#ifdef AGB_TIMELINE
+// debug build only (-DAGB_TIMELINE): the clock64 timeline CTA 0 of damsm_bwd3_kernel recorded, and per-CTA run times
 extern "C" int agb_damsm_debug_timeline(long long* out, int n) {
   const size_t bytes = std::min((size_t)n * 8, sizeof(agb::tc::g_tl));
   return (int)cudaMemcpyFromSymbol(out, agb::tc::g_tl, bytes);
@@ -487,3 +472,4 @@ extern "C" int agb_damsm_debug_cta_times(long long* out, int n) {
   const size_t bytes = std::min((size_t)n * 8, sizeof(agb::tc::g_tl_cta));
   return (int)cudaMemcpyFromSymbol(out, agb::tc::g_tl_cta, bytes);
 }
+#endif

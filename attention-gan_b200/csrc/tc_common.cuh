@@ -47,6 +47,7 @@ struct TcGemmArgs {
   int nsrc;                    // 1, or 2: a second (A2, B2) operand pair continues the same reduction
   int64_t a2_zrow, b2_zrow;    // batch row offsets of the second pair
   int64_t a2_zcol, b2_zcol;    // batch column offsets of the second pair
+  int prof_tag;                // agb::ProfTag the launch is timed under (0 = PROF_DAMSM_TC_BWD)
   int NT0;                     // != 0 (MN-major B only): CTA column 0 covers NT0 output columns, the others NT each
 };
 int tc_gemm(const TcGemmArgs& g, const CUtensorMap& mapA, const CUtensorMap& mapB, int batch, cudaStream_t st);

@@ -11,6 +11,7 @@
 //
 // Warp roles: warp 4 = TMA producer, warp 5 = MMA issuer, warps 0-3 = epilogue (TMEM -> global).
 #include <algorithm>
+#include <atomic>
 
 #include "tc_common.cuh"
 
@@ -219,10 +220,14 @@ int tc_gemm2(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap&
   const int nt_max = std::max(g.NT, g.NT0);
   if (g.MT * nt_max > 512) return fail_arg("tc_gemm: MT*NT=%d exceeds TMEM", g.MT * nt_max);
   if (g.nsrc != 2) g.nsrc = 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AGB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-    attr_set = true;
+  {   // per device, once
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    AGB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_relaxed)) {
+      AGB_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+      if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_relaxed);
+    }
   }
   dim3 grid(g.NT0 ? 1 + cdiv(std::max(0, g.N - g.NT0), g.NT) : cdiv(g.N, g.NT), cdiv(g.M, 128 * g.MT), batch);
   if (grid.y > 65535 || grid.z > 65535) return fail_unsupported("tc_gemm grid too large");
@@ -233,7 +238,7 @@ int tc_gemm2(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap&
   const int max_stages = std::min(kGemmStages, (kGemmSmem - 1024) / stage_bytes);
   g.stages = (int)std::min<long long>(max_stages, std::max<long long>(2, chunks));
   const int smem_bytes = std::max(g.stages * stage_bytes, 128 * (nt_max + 1) * 4) + 1024;
-  const int slot = prof_begin(PROF_DAMSM_TC_BWD, st);
+  const int slot = prof_begin(g.prof_tag ? g.prof_tag : PROF_DAMSM_TC_BWD, st);
   tc_gemm_kernel<<<grid, 192, smem_bytes, st>>>(mapA, mapB, mapA2, mapB2, g);
   prof_end(slot, st);
   return check_launch("tc_gemm_kernel");

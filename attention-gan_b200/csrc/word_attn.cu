@@ -23,8 +23,8 @@ int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dct
                                int T, int io_dtype);
 int word_attn_bwd_tc_ctas(int B, int HW);
 int word_attn_bwd_tc_grid(int B, int HW);
-int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
-                     void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
+int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, int64_t dctx_bs,
+                     const void* dattn, void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
                      float scale, cudaStream_t st);
 }  // namespace tc
 
@@ -678,7 +678,7 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
   int G = 0;                                      // 0: every partial slot is valid
   if (use_tc) {
     G = tc::word_attn_bwd_tc_grid(B, HW);
-    rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dattn, dimages, part, ntiles, nullptr, B, C, HW, T, io_dtype, scale, st);
+    rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dctx_bs, dattn, dimages, part, ntiles, nullptr, B, C, HW, T, io_dtype, scale, st);
     if (rc) return rc;
   } else {
     AGB_DISPATCH_TMAX(tm, {

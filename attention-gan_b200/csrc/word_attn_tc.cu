@@ -48,6 +48,13 @@ template <typename T16> __device__ __forceinline__ T16 f2h(float v);
 template <> __device__ __forceinline__ __half f2h<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 f2h<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// ablation switches exist only in -DAGB_ABLATION builds (timing experiments; results are wrong when set)
+#ifdef AGB_ABLATION
+#define AGB_ABL(p, bit) ((p).dbg & (bit))
+#else
+#define AGB_ABL(p, bit) (false)
+#endif
+
 struct AttnFwdParams {
   const float* we;        // [B, C, T] fp32 projected words
   const int64_t* mask;    // [B, T]
@@ -259,7 +266,7 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
     for (long long g = g0; g < g1;) {
       const Segment sg = next_segment(g, g1, p.tiles);
       const int b = sg.b;
-      const int ntile = ((p.dbg & 16) && warp != 1) ? 0 : sg.n;
+      const int ntile = (AGB_ABL(p, 16) && warp != 1) ? 0 : sg.n;
       // ---- operands of this sample: W.e hi + lo 16-bit split, K-major swizzled rows; mask bias ----
       {
         const float* we = p.we + (size_t)b * C * p.T;
@@ -298,7 +305,7 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
           // event-driven issue: GEMM1 of tile j1 needs its h tile and the TMEM buffer (output warps done
           // with tile j1 - 2); GEMM2 of tile j2 needs P from the softmax warps.  Neither blocks the other.
           int j1 = 0, j2 = 0;
-          if (p.dbg & 16) {                       // tuning: pure TMA streaming rate
+          if (AGB_ABL(p, 16)) {                       // tuning: pure TMA streaming rate
             for (int j = 0; j < ntile; ++j) {
               mbar_wait(&h_full[(it0 + j) % nst], ((it0 + j) / nst) & 1);
               mbar_arrive(&h_empty[(it0 + j) % nst]);
@@ -349,7 +356,7 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
           const int it = it0 + j, u = it & 1, k = it >> 1;
           mbar_wait(&s_full[u], k & 1);
           tc_fence_after();
-          if (p.dbg & 4) {
+          if (AGB_ABL(p, 4)) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_ready[u]);
@@ -404,7 +411,7 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
           const int it = it0 + j, u = it & 1, k = it >> 1;
           mbar_wait(&c_full[u], k & 1);
           tc_fence_after();
-          if (p.dbg & 8) {
+          if (AGB_ABL(p, 8)) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&c_empty[u]);
@@ -441,7 +448,7 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
             IO* dst = ctx + (size_t)sc.row * p.HW + pix;
 #pragma unroll
             for (int i = 0; i < C / 8; ++i) {
-              if (pix < p.HW && !(p.dbg & 1)) *reinterpret_cast<uint4*>(dst) = lds128(sc.ld + i * 1024);
+              if (pix < p.HW && !AGB_ABL(p, 1)) *reinterpret_cast<uint4*>(dst) = lds128(sc.ld + i * 1024);
               dst += row8;
             }
           }
@@ -450,7 +457,7 @@ word_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const AttnFwdP
             IO* dst = attn + (size_t)sa.row * p.HW + pix;
 #pragma unroll
             for (int i = 0; i < KB; ++i) {
-              if (sa.row + 8 * i < p.T && pix < p.HW && !(p.dbg & 2)) *reinterpret_cast<uint4*>(dst) = lds128(sa.ld + i * 1024);
+              if (sa.row + 8 * i < p.T && pix < p.HW && !AGB_ABL(p, 2)) *reinterpret_cast<uint4*>(dst) = lds128(sa.ld + i * 1024);
               dst += row8;
             }
           }
@@ -477,13 +484,13 @@ static int launch_attn_fwd_tc_c(const CUtensorMap& mapH, const AttnFwdParams& p_
   // deepest h-tile ring that still lets per_sm CTAs share the SM's 227 KB (1 KB reserved per CTA)
   int stages = ((227 * 1024) / per_sm - 1024 - fixed) / (2 * CT * 128);
   stages = std::max(2, std::min(kMaxAttnStages, stages));
-  if (const char* e = getenv("AGB_ATTN_FWD_STAGES")) stages = std::max(2, std::min(kMaxAttnStages, atoi(e)));   // tuning knob
+  if (options().attn_fwd_stages > 0) stages = std::max(2, std::min(kMaxAttnStages, options().attn_fwd_stages));   // tuning knob
   AttnFwdParams p = p_in;
   p.stages = stages;
   const int smem = stages * 2 * CT * 128 + fixed;
   int grid = persistent_grid((long long)sms * per_sm, p.B, p.tiles);
-  if (const char* e = getenv("AGB_ATTN_FWD_CTAS"))   // tuning knob
-    grid = (int)std::min<long long>(std::max(1, atoi(e)), (long long)p.B * p.tiles);
+  if (options().attn_fwd_ctas > 0)   // tuning knob
+    grid = (int)std::min<long long>(options().attn_fwd_ctas, (long long)p.B * p.tiles);
 #define AGB_ATTN_FWD_CASE(NTV, TLV)                                                              \
   {                                                                                               \
     auto kern = word_attn_fwd_tc_kernel<IO, NTV, TLV, CT>;                                        \
@@ -510,9 +517,7 @@ static int launch_attn_fwd_tc(const void* images, const AttnFwdParams& p, cudaSt
   if (int rc = make_tmap_2d(&mapH, images, (uint64_t)p.B * p.C, (uint64_t)p.HW, (uint32_t)p.C,
                             std::is_same<IO, __nv_bfloat16>::value))
     return rc;
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sms();
   const int slot = prof_begin(PROF_ATTN_FWD, st);
   int rc = 0;
   switch (p.C) {
@@ -550,6 +555,7 @@ struct AttnBwdParams {
   int B, C, HW, T;
   float scale;
   int tiles, ctas_per_sample;
+  int d_rows;             // rows of the dctx tensor map per sample (= dctx batch stride / HW; C when contiguous)
 };
 
 constexpr int kBwdNT = 32;
@@ -641,9 +647,9 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
           mbar_wait(&in_empty[s], (use & 1) ^ 1);
           mbar_expect_tx(&in_full[s], (uint32_t)stage_bytes);
           unsigned char* st = sIn + s * stage_bytes;
-          tma_load_2d(st, &mapD, &in_full[s], px0, sg.b * C);
+          tma_load_2d(st, &mapD, &in_full[s], px0, sg.b * p.d_rows);
           tma_load_2d(st + box, &mapH, &in_full[s], px0, sg.b * C);
-          tma_load_2d(st + 2 * box, &mapD, &in_full[s], px0 + 64, sg.b * C);
+          tma_load_2d(st + 2 * box, &mapD, &in_full[s], px0 + 64, sg.b * p.d_rows);
           tma_load_2d(st + 3 * box, &mapH, &in_full[s], px0 + 64, sg.b * C);
         }
         g += sg.n;
@@ -897,18 +903,17 @@ int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dct
                                int T, int io_dtype) {
   if (io_dtype != AGB_BF16 && io_dtype != AGB_F16) return 0;
   if ((C != 16 && C != 32) || T > kBwdNT || HW % 8 != 0) return 0;
-  if (dctx_bs != (int64_t)C * HW) return 0;
+  // dctx may be a channel slice of a wider [B, C', HW] gradient (GenNextStage's concat buffer): whole rows only
+  if (dctx_bs < (int64_t)C * HW || dctx_bs % HW != 0) return 0;
   if ((((uintptr_t)images | (uintptr_t)dctx) & 15) != 0) return 0;
   return 1;
 }
 
 // persistent grid of the backward kernel: 2 CTAs per SM, never more CTAs than tiles
 int word_attn_bwd_tc_grid(int B, int HW) {
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (const char* e = getenv("AGB_ATTN_BWD_CTAS"))   // tuning knob
-    return (int)std::min<long long>(std::max(1, atoi(e)), (long long)B * cdiv(HW, 128));
+  const int sms = device_sms();
+  if (options().attn_bwd_ctas > 0)   // tuning knob
+    return (int)std::min<long long>(options().attn_bwd_ctas, (long long)B * cdiv(HW, 128));
   return persistent_grid((long long)sms * 2, B, cdiv(HW, 128));
 }
 
@@ -934,18 +939,20 @@ __global__ void sum_range_partials_kernel(const float* __restrict__ part, int sl
   out[(size_t)b * n + i] = acc;
 }
 
-int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, const void* dattn,
-                     void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
+int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, int64_t dctx_bs,
+                     const void* dattn, void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
                      float scale, cudaStream_t st) {
   const bool bf = io_dtype == AGB_BF16;
   CUtensorMap mapH, mapD;
   if (int rc = make_tmap_2d(&mapH, images, (uint64_t)B * C, (uint64_t)HW, (uint32_t)C, bf)) return rc;
-  if (int rc = make_tmap_2d(&mapD, dctx, (uint64_t)B * C, (uint64_t)HW, (uint32_t)C, bf)) return rc;
+  const int d_rows = (int)(dctx_bs / HW);
+  if (int rc = make_tmap_2d(&mapD, dctx, (uint64_t)(B - 1) * d_rows + C, (uint64_t)HW, (uint32_t)C, bf)) return rc;
   AttnBwdParams p;
   p.we = we; p.mask = mask; p.dattn = dattn; p.dh = dimages; p.part = part;
   p.B = B; p.C = C; p.HW = HW; p.T = T; p.scale = scale;
   p.tiles = cdiv(HW, 128);
   p.ctas_per_sample = 0;
+  p.d_rows = d_rows;
   p.part_slots = part_slots;
   const int NT = kBwdNT;
   const int TL = (T + 7) / 8 * 8;
@@ -953,7 +960,7 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
   // deepest input ring that still lets two CTAs share the SM's 227 KB (1 KB reserved per CTA)
   int stages = ((227 * 1024) / 2 - 1024 - fixed) / (4 * C * 128);
   stages = std::max(2, std::min(kMaxBwdStages, stages));
-  if (const char* e = getenv("AGB_ATTN_BWD_STAGES")) stages = std::max(2, std::min(kMaxBwdStages, atoi(e)));   // tuning knob
+  if (options().attn_bwd_stages > 0) stages = std::max(2, std::min(kMaxBwdStages, options().attn_bwd_stages));   // tuning knob
   p.stages = stages;
   const int smem = stages * 4 * C * 128 + fixed;
   const int grid = word_attn_bwd_tc_grid(B, HW);
@@ -1006,7 +1013,9 @@ int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, v
   p.tiles = cdiv(HW, 128);
   p.ctas_per_sample = 0;   // the forward kernel is persistent over all samples
   p.dbg = 0;
+#ifdef AGB_ABLATION
   if (const char* e = getenv("AGB_ATTN_DEBUG")) p.dbg = atoi(e);
+#endif
   if (io_dtype == AGB_BF16) return launch_attn_fwd_tc<__nv_bfloat16>(images, p, st);
   return launch_attn_fwd_tc<__half>(images, p, st);
 }

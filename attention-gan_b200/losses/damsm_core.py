@@ -25,8 +25,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from agb_native import native
-from agb_native import ops as native_ops
+from ..agb_native import native
+from ..agb_native import ops as native_ops
 
 
 @dataclass
@@ -40,6 +40,10 @@ class DamsmConfig:
     group: Any = None          # torch.distributed process group, or None for a single process
     ops: Any = native_ops
     want_att: bool = True
+    # sharded runs only: the caption length every rank pads its word features to before the all-gather.  The
+    # reference's RNN pads to the LOCAL batch's longest caption (rnn_encoder.py:89-92), so T may differ per rank;
+    # None = agree on max(T) with one all-reduce per step (a host sync), an int = no sync (must be >= every T)
+    max_words: Optional[int] = None
 
 
 def _world(group) -> int:
@@ -72,10 +76,23 @@ def _reduce_scatter_sum(t: torch.Tensor, group) -> torch.Tensor:
     return t[k * n:(k + 1) * n].clone()
 
 
+def _agree_on_words(T_local: int, cfg: "DamsmConfig", device) -> int:
+    """the caption length all ranks pad to (see DamsmConfig.max_words)"""
+    if cfg.max_words is not None:
+        if T_local > cfg.max_words:
+            raise RuntimeError(f"words_emb has T={T_local} > max_words={cfg.max_words}")
+        return int(cfg.max_words)
+    t = torch.tensor([T_local], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=cfg.group)
+    return int(t.item())
+
+
 def as_device_i32(x, device) -> Optional[torch.Tensor]:
     """cap_lens arrive as a device tensor (words_loss.py:41), class_ids as numpy (words_loss.py:45)"""
     if x is None:
         return None
+    if torch.is_tensor(x) and x.dtype == torch.int32 and x.device == torch.device(device) and x.is_contiguous():
+        return x                                           # already resident (a step helper uploads it once)
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(np.ascontiguousarray(x.astype(np.int32)))
     elif not torch.is_tensor(x):
@@ -107,8 +124,13 @@ class _WordsLossFn(torch.autograd.Function):
         Bl, D = img.shape[0], img.shape[1]
         img3 = img.detach().float().reshape(Bl, D, -1).contiguous()
         w32 = words.detach().float()
+        T_local = w32.shape[2]
         if ex.W > 1:
-            w32 = _gather_cat(w32.transpose(1, 2), cfg.group).transpose(1, 2)    # [B,D,T] view of [B,T,D]
+            T_all = _agree_on_words(T_local, cfg, w32.device)
+            wt = w32.transpose(1, 2)                                             # [Bl,T,D]
+            if T_all != T_local:                                                 # zero slots: cap_lens masks them
+                wt = torch.nn.functional.pad(wt, (0, 0, 0, T_all - T_local))
+            w32 = _gather_cat(wt, cfg.group).transpose(1, 2)                     # [B,D,T] view of [B,T,D]
         fuse_sent = cnn is not None
         if fuse_sent:
             cnn32 = cnn.detach().float().reshape(Bl, -1).contiguous()
@@ -126,10 +148,12 @@ class _WordsLossFn(torch.autograd.Function):
         loss, dm = o.contrastive(m_all, ex.cls, ex.labels, cfg.gamma3, cfg.lam, ex.row0, Bl)
         ctx.save_for_backward(img3, w32, dm, m)
         ctx.cfg, ctx.ex = cfg, ex
-        ctx.meta = (img.shape, img.dtype, words.dtype)
+        ctx.meta = (img.shape, img.dtype, words.dtype, T_local)
         outs = [loss.reshape(())]
         if att is None:
             att = torch.empty(0, device=img.device)
+        elif att.shape[1] != T_local:
+            att = att[:, :T_local].contiguous()                                  # rows t >= L are zero anyway
         outs.append(att)
         if fuse_sent:
             outs.append(scos)
@@ -142,7 +166,7 @@ class _WordsLossFn(torch.autograd.Function):
     def backward(ctx, dloss, *unused):
         img3, w32, dm, m = ctx.saved_tensors
         cfg, ex = ctx.cfg, ctx.ex
-        ishape, idt, wdt = ctx.meta
+        ishape, idt, wdt, T_local = ctx.meta
         need_w = ctx.needs_input_grad[1]
         gscale = dloss.detach().float().reshape(1).contiguous()
         dimg, dwords = cfg.ops.damsm_bwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, dm, gscale, need_w,
@@ -151,7 +175,7 @@ class _WordsLossFn(torch.autograd.Function):
         if dwords is not None:
             if ex.W > 1:
                 dwords = _reduce_scatter_sum(dwords, cfg.group)
-            dwords = dwords.transpose(1, 2).to(wdt)                              # [Bl,D,T] like words_emb
+            dwords = dwords[:, :T_local].transpose(1, 2).to(wdt)                 # [Bl,D,T] like words_emb
         dimg = dimg.reshape(ishape).to(idt) if ctx.needs_input_grad[0] else None
         return dimg, dwords, None, None, None, None
 

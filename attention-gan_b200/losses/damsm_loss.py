@@ -3,16 +3,17 @@ train.py:140-141).  Not part of the reference API: a convenience for callers tha
 ``WordsLoss`` and ``SentenceLoss`` together; the results equal calling the two drop-ins."""
 from __future__ import annotations
 
-from agb_native import native
+from ..agb_native import native
 from .damsm_core import DamsmConfig, damsm_losses, split_att_maps
 
 
 class DAMSMLoss:
     def __init__(self, device, gamma1=4.0, gamma2=5.0, gamma3=10.0, wlambda=5.0, slambda=5.0, *, math="fp32",
-                 process_group=None, att_maps="list", eps=1e-8):
+                 process_group=None, att_maps="list", eps=1e-8, max_words=None):
         self.device = device
         self.wcfg = DamsmConfig(float(gamma1), float(gamma2), float(gamma3), float(wlambda), float(eps),
-                                native.MATH_NAMES[math], process_group, want_att=att_maps is not None)
+                                native.MATH_NAMES[math], process_group, want_att=att_maps is not None,
+                                max_words=max_words)
         self.scfg = DamsmConfig(gamma3=float(gamma3), lam=float(slambda), eps=float(eps), group=process_group)
         self.att_maps = att_maps
 

@@ -12,12 +12,14 @@ Extra keyword-only options (all default to the reference behaviour):
                  global batch; see losses/damsm_core.py)
   att_maps       "list" (reference: list of [1, L_i, 17, 17]; needs cap_lens on the host)
                  | "packed" (one [B, T, 17, 17] tensor, no host sync) | None
+  max_words      sharded runs: the caption length all ranks pad to before the all-gather (the RNN pads to the
+                 LOCAL longest caption, so T may differ per rank); None = agree on max(T) per step (one sync)
 """
 from __future__ import annotations
 
 import torch
 
-from agb_native import native
+from ..agb_native import native
 from .damsm_core import DamsmConfig, split_att_maps, words_loss
 
 
@@ -25,7 +27,7 @@ class WordsLoss:
     """Loss between words and images"""
 
     def __init__(self, device, gamma1=4.0, gamma2=5.0, gamma3=10.0, wlambda=5.0, *, math="fp32",
-                 process_group=None, att_maps="list"):
+                 process_group=None, att_maps="list", max_words=None):
         self.device = device
         self.gamma1 = gamma1
         self.gamma2 = gamma2
@@ -34,6 +36,7 @@ class WordsLoss:
         self.math = math
         self.process_group = process_group
         self.att_maps = att_maps
+        self.max_words = max_words
 
     def cosine_similarity(self, x1, x2, dim=1, eps=1e-8):
         """Returns cosine similarity between x1 and x2, computed along dim (words_loss.py:20-27).
@@ -46,7 +49,8 @@ class WordsLoss:
     def _config(self) -> DamsmConfig:
         return DamsmConfig(gamma1=float(self.gamma1), gamma2=float(self.gamma2), gamma3=float(self.gamma3),
                            lam=float(self.wlambda), eps=1e-8, math=native.MATH_NAMES[self.math],
-                           group=self.process_group, want_att=self.att_maps is not None)
+                           group=self.process_group, want_att=self.att_maps is not None,
+                           max_words=self.max_words)
 
     def get_loss(self, img_features, words_emb, labels, cap_lens, class_ids):
         """

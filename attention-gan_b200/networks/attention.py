@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from agb_native import ops
+from ..agb_native import ops
 
 GlobalAttention = None  # set below (BASELINE.json's name for AttentionModule)
 
@@ -57,6 +57,56 @@ class _WordAttention(torch.autograd.Function):
         return (dimages if need_img else None), dwords, dweight, None, None
 
 
+class _WordAttentionInto(torch.autograd.Function):
+    """the same fused attention, writing  cat((images, context), 1)  into a caller-owned [B, 2C, H, W] buffer:
+    the context leaves the kernel at channel offset C (ctx batch stride 2C*H*W in the C ABI), so GenNextStage's
+    torch.cat (generator_submodules.py:116) costs one copy of `images` instead of re-reading and re-writing both"""
+
+    @staticmethod
+    def forward(ctx, images, words, weight, mask, scaled, out, want_attn):
+        B, C, H, W = images.shape
+        if out.shape != (B, 2 * C, H, W) or out.dtype != images.dtype or not out.is_contiguous():
+            raise RuntimeError("forward_into: `out` must be a contiguous [B, 2*C, H, W] tensor of the images' dtype")
+        w32 = words if words.dtype == torch.float32 else words.float()
+        wt = weight.reshape(weight.shape[0], -1)
+        wt32 = (wt if wt.dtype == torch.float32 else wt.float()).contiguous()
+        m64 = (mask if mask.dtype == torch.int64 else mask.to(torch.int64)).to(images.device).contiguous()
+        out[:, :C].copy_(images.detach())
+        _, attn, we = ops.word_attn_fwd(images.detach(), w32.detach(), wt32.detach(), m64, scaled, want_attn,
+                                        ctx_out=out[:, C:])
+        ctx.mark_dirty(out)
+        ctx.save_for_backward(images, w32, wt32, m64, we)
+        ctx.scaled = scaled
+        ctx.meta = (words.dtype, weight.dtype, weight.shape, C)
+        ctx.set_materialize_grads(False)
+        if attn is None:
+            attn = torch.empty(0, device=images.device, dtype=images.dtype)
+            ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, dout, dattn):
+        images, w32, wt32, m64, we = ctx.saved_tensors
+        wdt, wtdt, wshape, C = ctx.meta
+        need_img, need_words, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if dout is None:
+            return None, None, None, None, None, None, None
+        dout = dout.to(images.dtype)
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        # d context is the second channel half of d out, read in place through its batch stride
+        dimages, dwords, dweight = ops.word_attn_bwd(images, w32, wt32, m64, we, dout[:, C:],
+                                                     None if dattn is None else dattn.to(images.dtype),
+                                                     ctx.scaled, need_words, need_w)
+        if need_img:
+            dimages += dout[:, :C]                       # the identity half of the concatenation
+        if dwords is not None:
+            dwords = dwords.to(wdt)
+        if dweight is not None:
+            dweight = dweight.reshape(wshape).to(wtdt)
+        return (dimages if need_img else None), dwords, dweight, None, None, None, None
+
+
 class AttentionModule(nn.Module):
     """Word-context attention of the generator's refinement stages
     (reference networks/attention.py:15-79; called from generator_submodules.py:113-114)."""
@@ -78,6 +128,18 @@ class AttentionModule(nn.Module):
             raise AttributeError("AttentionModule.forward called before apply_mask(mask)")
         ops.require_cuda(images, words, self.conv1.weight)
         return _WordAttention.apply(images, words, self.conv1.weight, self.mask, bool(scaled))
+
+
+    def forward_into(self, images, words, out, scaled=True, want_attn=True):
+        """images [B, C, H, W], words [B, E, T], out [B, 2C, H, W] (pre-allocated, contiguous) ->
+        (out, attn [B, T, H, W] or None) with  out == torch.cat((images, context), 1)  -- what GenNextStage builds
+        right after the attention call (generator_submodules.py:113-116).  Not part of the reference API."""
+        if self.mask is None:
+            raise AttributeError("AttentionModule.forward_into called before apply_mask(mask)")
+        ops.require_cuda(images, words, self.conv1.weight, out)
+        res, attn = _WordAttentionInto.apply(images, words, self.conv1.weight, self.mask, bool(scaled), out,
+                                             bool(want_attn))
+        return res, (attn if want_attn else None)
 
 
 GlobalAttention = AttentionModule

@@ -2,21 +2,34 @@
 """Benchmark of the word-region attention hot path (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                    [--workload cfg2|cfg4|cfg3|cfg1] [--math fp32|f16|bf16] [--batch B]
+                    [--workload cfg4|cfg2|cfg3|cfg5|cfg1] [--math fp32|f16|bf16] [--batch B] [--no-secondary]
 
-One "step" is one pass of the hot path over one batch of synthetic input:
-  cfg2 (default at N=1)  DAMSM WordsLoss + SentenceLoss forward+backward, batch 48, 17x17 regions,
-                         T=18, D=256 (grads w.r.t. region features, word embeddings, both codes)
-  cfg4 (default at N>1)  the same step at global batch 2048 sharded over the N ranks (word features
-                         all-gathered over NCCL so the negatives span the global batch); strong scaling
-  cfg3 / cfg1            generator word attention forward+backward (bf16 B=64, stages 64x64+128x128+256x256 / fp32 B=16 64x64)
+One "step" is one pass of the hot path over one batch of synthetic input.  The DEFAULT workload, at every N, is
+BASELINE.json configs[3] -- the configuration the headline metric is quoted on:
+
+  cfg4   DAMSM WordsLoss + SentenceLoss forward+backward at GLOBAL batch 2048 (17x17 regions, T=18, D=256; grads
+         w.r.t. region features, word embeddings and both sentence codes), sharded over the N ranks with the word
+         features all-gathered over NCCL so the negatives span the global batch.  Strong scaling: N=1 computes all
+         2048 x 2048 pairs on one GPU, so the driver's 1/2/4/8 curve is ONE workload.
+  cfg2   the same step at batch 48 (configs[1])
+  cfg3   generator word attention forward+backward, bf16, batch 64, stages 64x64 + 128x128 + 256x256 (configs[2])
+  cfg5   long-caption stress: T=64 words, 256x256, bf16, batch 256 split over the ranks (configs[4]; 32 per GPU)
+  cfg1   attention fp32, batch 16, 64x64 (configs[0])
+
+At N=1 the default run also measures cfg2, cfg3 and one GPU's share of cfg5 and reports them under "secondary"
+in the same JSON line (pairs/s, pixels/s, HBM fraction).
+
 Metric: pairs/s (image-caption pairs) for the DAMSM step, pixels/s for the attention workloads.
-
-`value` is measured with inputs resident in HBM; `e2e` through the public drop-in API with pinned
-HOST inputs (host->device copies and the device->host read of the losses inside the timed region).
-`roofline` is for the dominant kernel, timed live with CUDA events on its launching stream
-(agb_prof_* hooks); `cpu_baseline` / `--impl reference` time the oracle port of the reference
-(the reference itself is Python and does not travel to the GPU box) on the host cores.
+`value`   inputs resident in HBM; the whole step replayed from a CUDA graph in a single process (the product's
+          GraphedStep helper), eager launches under torchrun; `eager` gives the un-graphed time next to it.
+`e2e`     the same step through the public drop-in API from pinned HOST inputs: host->device copies of every input
+          and the device->host read of the losses inside the timed region (`e2e_eager`: without the graph).
+`roofline` per kernel, timed live with CUDA events on the launching stream (agb_prof_* hooks) in an eager pass:
+          algorithmic flops (or bytes) of the launches / their summed duration; nothing is summed across
+          concurrently running kernels.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference (the reference is Python under /root/reference,
+          which does not exist on the GPU box) on the host cores, on a bounded sample of the same workload;
+`torch_eager_gpu`: the same op-by-op port on cuda:0 (PyTorch ATen/cuBLAS eager), the second baseline of SURVEY 8d.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -35,15 +48,39 @@ sys.path.insert(0, ROOT)
 
 R_, T_, D_ = 289, 18, 256
 L2_FLUSH_BYTES = 256 << 20
+CFG_BATCH = {"cfg2": 48, "cfg4": 2048}
+METRIC_DAMSM = "damsm_words_sentence_loss_fwd_bwd_pairs_per_sec"
+METRIC_ATTN = "word_attention_fwd_bwd_pixels_per_sec"
+# algorithmic GEMM units (2*R*L*D flop each) per (image, caption) pair and kernel, SURVEY 8d / DESIGN.md section 4
+DAMSM_KERNELS = {2: ("damsm_fwd2_kernel (scores + context, both softmaxes, cosine, LSE)", 2),
+                 3: ("damsm_bwd3_kernel (d beta GEMM + both softmax backwards)", 1),
+                 6: ("tc_gemm_kernel d img (dC via beta + dC via ds)", 2),
+                 7: ("tc_gemm_kernel d words (dW via ds)", 1)}
 
 
-def load_traffic(workload):
-    """measured DRAM bytes per step of the dominant kernels (committed ncu capture), or None"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as fh:
-            return json.load(fh)[workload]["bytes_per_step"]
-    except Exception:
-        return None
+def workload_name(wl, Bg=None, world=1):
+    if wl in ("cfg2", "cfg4"):
+        Bg = Bg or CFG_BATCH[wl]
+        return (f"{wl}: DAMSM WordsLoss+SentenceLoss fwd+bwd, global batch {Bg}, R=289, T=18 (cap_lens U{{2..18}}), "
+                f"D=256, class_ids U{{0..499}}")
+    if wl == "cfg3":
+        return "cfg3: AttentionModule fwd+bwd, batch 64, feature maps 64x64 + 128x128 + 256x256, T=18, C=32, E=256, bf16 I/O"
+    if wl == "cfg5":
+        return "cfg5: AttentionModule fwd+bwd, long captions T=64, 256x256, C=32, E=256, bf16 I/O, global batch 256"
+    return "cfg1: AttentionModule fwd+bwd, batch 16, 64x64, T=18, C=32, E=256, fp32 I/O"
+
+
+def load_traffic(key):
+    """measured DRAM bytes per launch of the dominant kernel (committed ncu --set full capture), or None"""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                d = json.load(fh)
+            if key in d:
+                return d[key].get("bytes_per_launch", d[key].get("bytes_per_step"))
+        except Exception:
+            continue
+    return None
 
 
 def load_peaks():
@@ -51,9 +88,9 @@ def load_peaks():
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             p = json.load(fh)
         return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
-                    tf_sust=float(p["bf16_tflops_sustained"]), source="measured")
+                    tf_sust=float(p["bf16_tflops_sustained"]), source="MEASURED_PEAKS.json")
     except Exception:
-        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="B200_PROFILING.md fallback")
 
 
 class ClockSampler:
@@ -100,16 +137,34 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference on the host cores
+# synthetic inputs: ONE recipe for both arms (the reference arm takes the first rows of the same global batch)
 # ------------------------------------------------------------------------------------------------
-def cpu_damsm_step(B, seed=0):
+def damsm_inputs(Bg):
+    """the global batch of cfg2 / cfg4 from one seed: features ~ N(0,1), cap_lens ~ U{2..18} with one
+    caption of full length, class_ids ~ U{0..499} (k = 500 finest clusters, data/bedrooms.py:291-304)"""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(Bg, D_, 17, 17, generator=g)
+    wrd = torch.randn(Bg, T_, D_, generator=g)                      # physical [B,T,D] (rnn_encoder.py:91-92)
+    cnn = torch.randn(Bg, D_, generator=g)
+    rnn = torch.randn(Bg, D_, generator=g)
+    lens = torch.randint(2, T_ + 1, (Bg,), generator=g, dtype=torch.int64)
+    lens[0] = T_
+    cls = torch.randint(0, 500, (Bg,), generator=g, dtype=torch.int64)
+    return img, wrd, cnn, rnn, lens, cls
+
+
+def ref_damsm_step(B, Bg, device="cpu"):
+    """WordsLoss + SentenceLoss fwd+bwd of the op-by-op port on the first B samples of the global batch"""
     import torch
     from oracle import ref_port as rp
-    img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, T=T_, D=D_, hw=17, seed=seed, n_classes=max(2, B // 4))
-    img.requires_grad_(True)
-    wrd = wrd.detach().clone().requires_grad_(True)
-    cnn.requires_grad_(True)
-    rnn.requires_grad_(True)
+    img, wrd, cnn, rnn, lens, cls = damsm_inputs(Bg)
+    img = img[:B].to(device).requires_grad_(True)
+    wrd = wrd[:B].to(device).transpose(1, 2).detach().requires_grad_(True)
+    cnn = cnn[:B].to(device).requires_grad_(True)
+    rnn = rnn[:B].to(device).requires_grad_(True)
+    lens, cls = lens[:B], cls[:B].numpy()
+    labels = torch.arange(B, device=device)
 
     def step():
         for t in (img, wrd, cnn, rnn):
@@ -117,18 +172,19 @@ def cpu_damsm_step(B, seed=0):
         wl, _ = rp.words_loss(img, wrd, labels, lens, cls)
         sl = rp.sentence_loss(cnn, rnn, labels, cls)
         (wl + sl).backward()
-        return float(wl) + float(sl)
+        return float(wl.detach()) + float(sl.detach())
     return step, B * B
 
 
-def cpu_attn_step(B, C, E, T, hw, seed=0):
+def ref_attn_step(B, C, E, T, hw, device="cpu"):
     import torch
     from oracle import ref_port as rp
-    images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed)
-    images.requires_grad_(True)
-    words = words.detach().clone().requires_grad_(True)
-    weight.requires_grad_(True)
-    dctx = torch.randn(B, C, hw, hw)
+    images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, 0)
+    images = images.to(device).requires_grad_(True)
+    words = words.to(device).detach().clone().requires_grad_(True)
+    weight = weight.to(device).requires_grad_(True)
+    mask = mask.to(device)
+    dctx = torch.randn(B, C, hw, hw, generator=torch.Generator().manual_seed(1)).to(device)
 
     def step():
         for t in (images, words, weight):
@@ -139,43 +195,50 @@ def cpu_attn_step(B, C, E, T, hw, seed=0):
     return step, B * hw * hw
 
 
-def time_cpu(step, steps, warmup):
+def time_host(step, steps, warmup, sync=None):
     for _ in range(warmup):
         step()
+    if sync:
+        sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
+    if sync:
+        sync()
     return (time.perf_counter() - t0) / steps
 
 
 def run_reference(args):
+    """reference arm: the reference's CPU implementation of the path (oracle port) on the host cores, rank 0 only"""
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    if args.workload in ("cfg2", "cfg4"):
-        B = 48 if args.workload == "cfg2" else 96
-        step, units = cpu_damsm_step(B)
-        metric, unit = "damsm_words_sentence_loss_fwd_bwd_pairs_per_sec", "pairs/s"
-        sample = (f"oracle/ref_port.py (op-by-op torch-CPU port of the reference) WordsLoss+SentenceLoss fwd+bwd, "
-                  f"B={B} (R=289,T=18,D=256), fp32" + ("" if args.workload == "cfg2" else
-                                                      "; bounded sample of the global-batch-2048 workload"))
-        workload = "cfg2: DAMSM words+sentence loss fwd+bwd, B=48, R=289, T=18, D=256" if args.workload == "cfg2" \
-            else "cfg4: DAMSM step, global batch 2048 (CPU arm: per-pair rate on a B=96 sample)"
+    wl = args.workload
+    if wl in ("cfg2", "cfg4"):
+        Bg = args.batch or CFG_BATCH[wl]
+        B = min(Bg, 48 if wl == "cfg2" else 96)
+        step, units = ref_damsm_step(B, Bg)
+        metric, unit = METRIC_DAMSM, "pairs/s"
+        sample = (f"oracle/ref_port.py (op-by-op torch-CPU port of the reference) WordsLoss+SentenceLoss fwd+bwd on the "
+                  f"first {B} samples of the workload's global batch ({B}x{B} pairs per step), fp32, all host threads")
     else:
-        B, C, E, T, hw = (16, 32, 256, 18, 64) if args.workload == "cfg1" else (4, 32, 256, 18, 128)
-        step, units = cpu_attn_step(B, C, E, T, hw)
-        metric, unit = "word_attention_fwd_bwd_pixels_per_sec", "pixels/s"
-        sample = f"oracle/ref_port.py word_attention fwd+bwd fp32, B={B}, {hw}x{hw}, T={T}, C={C}"
-        workload = f"{args.workload}: generator word attention fwd+bwd (CPU arm: B={B}, {hw}x{hw}, fp32)"
-    sec = time_cpu(step, args.steps, args.warmup)
+        if wl == "cfg1":
+            B, C, E, T, hw = 16, 32, 256, 18, 64
+        elif wl == "cfg5":
+            B, C, E, T, hw = 1, 32, 256, 64, 256
+        else:
+            B, C, E, T, hw = 4, 32, 256, 18, 128
+        step, units = ref_attn_step(B, C, E, T, hw)
+        metric, unit = METRIC_ATTN, "pixels/s"
+        sample = f"oracle/ref_port.py word_attention fwd+bwd, fp32, B={B}, {hw}x{hw}, T={T}, C={C}, all host threads"
+    sec = time_host(step, args.steps, args.warmup)
     v = units / sec
     line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload},
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong" if wl in ("cfg4", "cfg5") else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(wl, args.batch)},
             "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -186,307 +249,389 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
-def prof_read(lib, tag):
-    ms = ctypes.c_double(0.0)
-    n = ctypes.c_longlong(0)
-    lib.agb_prof_read(tag, ctypes.byref(ms), ctypes.byref(n))
-    return ms.value, n.value
+class Env:
+    """per-process measurement context: device, ranks, timing helpers"""
 
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.group = dist.group.WORLD
+        import attention_gan_b200 as pkg
+        self.pkg = pkg
+        self.lib = pkg.native.lib()
+        self.flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=self.dev)
 
-def run_native(args):
-    import torch
-    import torch.distributed as dist
-    import attention_gan_b200 as pkg
-    from oracle import ref_port as rp          # seeded input generators only (bench may use oracle/ as a checker)
+    def l2_flush(self):
+        self.flush.zero_()                    # write a buffer larger than the 126 MB L2: evicts every input line
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    group = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-    lib = pkg.native.lib()
-    peaks = load_peaks()
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
-    flush_mode = os.environ.get("AGB_BENCH_FLUSH", "write")
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def l2_flush():
-        # write a buffer larger than L2 (evicts every input line)
-        flush.zero_()
-        if flush_mode == "write_read":
-            # diagnostic: then stream a clean buffer through L2 so no dirty lines remain
-            flush_rd.sum()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    damsm = args.workload in ("cfg2", "cfg4")
-    if damsm:
-        Bg = args.batch or (48 if args.workload == "cfg2" else 2048)
-        assert Bg % world == 0
-        Bl = Bg // world
-        # every rank generates the same global batch from one seed and keeps its shard
-        g = torch.Generator().manual_seed(0)
-        sl = slice(rank * Bl, rank * Bl + Bl)
-        img_h = torch.randn(Bg, D_, 17, 17, generator=g)[sl].contiguous().pin_memory()
-        wrd_h = torch.randn(Bg, T_, D_, generator=g)[sl].contiguous().pin_memory()     # physical [B,T,D]
-        cnn_h = torch.randn(Bg, D_, generator=g)[sl].contiguous().pin_memory()
-        rnn_h = torch.randn(Bg, D_, generator=g)[sl].contiguous().pin_memory()
-        lens_h = torch.randint(2, T_ + 1, (Bg,), generator=g, dtype=torch.int64)
-        lens_h[0] = T_
-        mean_len = float(lens_h.float().mean())
-        lens_h = lens_h[sl].contiguous().pin_memory()
-        cls_np = torch.randint(0, 500, (Bg,), generator=g, dtype=torch.int64)[sl].numpy()
-        cls_h = torch.from_numpy(cls_np).to(torch.int32).pin_memory()
-        labels = torch.arange(Bl, device=dev)
-        loss_mod = pkg.DAMSMLoss(dev, math=args.math, process_group=group, att_maps="packed")
-        out_h = torch.empty(2, dtype=torch.float32).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in (img_h, wrd_h, cnn_h, rnn_h, lens_h, cls_h))
-        d2h = 8
-
-        def make_dev():
-            ts = [img_h.to(dev), wrd_h.to(dev), cnn_h.to(dev), rnn_h.to(dev)]
-            for t in ts:
-                t.requires_grad_(True)
-            return ts + [lens_h.to(dev), torch.from_numpy(cls_np).to(dev, torch.int32)]
-
-        def step_dev(ts):
-            img, wrd, cnn, rnn, lens, cls = ts
-            for t in (img, wrd, cnn, rnn):
-                t.grad = None
-            wl, sls, _ = loss_mod.get_losses(img, cnn, wrd.transpose(1, 2), rnn, labels, lens, cls)
-            (wl + sls).backward()
-            return wl, sls
-
-        def step_e2e():
-            ts = [img_h.to(dev, non_blocking=True).requires_grad_(True),
-                  wrd_h.to(dev, non_blocking=True).requires_grad_(True),
-                  cnn_h.to(dev, non_blocking=True).requires_grad_(True),
-                  rnn_h.to(dev, non_blocking=True).requires_grad_(True),
-                  lens_h.to(dev, non_blocking=True)]
-            img, wrd, cnn, rnn, lens = ts
-            wl, sls, _ = loss_mod.get_losses(img, cnn, wrd.transpose(1, 2), rnn, labels, lens,
-                                             cls_h.to(dev, non_blocking=True))
-            (wl + sls).backward()
-            out_h[0:1].copy_(wl.detach().reshape(1), non_blocking=True)
-            out_h[1:2].copy_(sls.detach().reshape(1), non_blocking=True)
-
-        units = Bl * Bg                       # pairs this rank computes per step
-        total_units = Bg * Bg
-        metric, unit = "damsm_words_sentence_loss_fwd_bwd_pairs_per_sec", "pairs/s"
-        workload = (f"{args.workload}: DAMSM WordsLoss+SentenceLoss fwd+bwd, global batch {Bg}"
-                    f"{' sharded over %d ranks' % world if world > 1 else ''}, R=289, T=18 (cap_lens U{{2..18}}), D=256, "
-                    f"class_ids U{{0..499}}, math={args.math}")
-        flop_per_unit = 12.0 * R_ * mean_len * D_
-        tc = args.math != "fp32"
-        tags = [2, 3] if tc else [1]
-        dtype = {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.math]
-    else:
-        if args.workload == "cfg1":
-            B, C, E, T, hws, tdt = 16, 32, 256, 18, [64], torch.float32
-        else:
-            # configs[2]: the generator's attention stages, 64x64 and 128x128 (generator.py:56,61) plus the
-            # synthetic 256x256 third stage of SURVEY 8d; one step = forward + backward of every stage
-            B, C, E, T, hws, tdt = 64, 32, 256, 18, [64, 128, 256], torch.bfloat16
-        if args.hw:
-            hws = [args.hw]
-        B = args.batch or B
-        assert B % world == 0
-        Bl = B // world
-        sl = slice(rank * Bl, rank * Bl + Bl)
-        g = torch.Generator().manual_seed(1)
-        img_h, dctx_h = [], []
-        for hw in hws:
-            images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed=0)
-            img_h.append(images[sl].to(tdt).contiguous().pin_memory())
-            dctx_h.append(torch.randn(B, C, hw, hw, generator=g)[sl].to(tdt).contiguous().pin_memory())
-            del images
-        wrd_h = words[sl].transpose(1, 2).contiguous().pin_memory()        # physical [B,T,E]
-        mask_d = mask[sl].to(dev)
-        mods = []
-        for hw in hws:                                                      # one AttentionModule per stage
-            mod = pkg.AttentionModule(C, E).to(dev)
-            with torch.no_grad():
-                mod.conv1.weight.copy_(weight.to(dev))
-            mod.apply_mask(mask_d)
-            mods.append(mod)
-        out_h = torch.empty(256 * len(hws), dtype=tdt).pin_memory()
-        h2d = sum(t.numel() * t.element_size() for t in (*img_h, *dctx_h, wrd_h))
-        d2h = out_h.numel() * out_h.element_size()
-
-        def make_dev():
-            return [[t.to(dev).requires_grad_(True) for t in img_h], wrd_h.to(dev).requires_grad_(True),
-                    [t.to(dev) for t in dctx_h]]
-
-        def step_dev(ts):
-            ims, wd, dctxs = ts
-            wd.grad = None
-            outs = []
-            for mod, im, dctx in zip(mods, ims, dctxs):
-                im.grad = None
-                mod.conv1.weight.grad = None
-                ctx, attn = mod(im, wd.transpose(1, 2))
-                ctx.backward(dctx)
-                outs.append((ctx, attn))
-            return outs
-
-        def step_e2e():
-            wd = wrd_h.to(dev, non_blocking=True).requires_grad_(True)
-            for i, (mod, im_h, dc_h) in enumerate(zip(mods, img_h, dctx_h)):
-                im = im_h.to(dev, non_blocking=True).requires_grad_(True)
-                dctx = dc_h.to(dev, non_blocking=True)
-                mod.conv1.weight.grad = None
-                ctx, attn = mod(im, wd.transpose(1, 2))
-                ctx.backward(dctx)
-                # read a slice of every stage's result back
-                out_h[256 * i:256 * (i + 1)].copy_(im.grad.reshape(-1)[:256], non_blocking=True)
-
-        npix = sum(hw * hw for hw in hws)
-        units = Bl * npix
-        total_units = B * npix
-        es = 4 if tdt == torch.float32 else 2
-        metric, unit = "word_attention_fwd_bwd_pixels_per_sec", "pixels/s"
-        workload = (f"{args.workload}: AttentionModule fwd+bwd, batch {B}, feature maps "
-                    f"{' + '.join('%dx%d' % (hw, hw) for hw in hws)}, T={T}, C={C}, E={E}, "
-                    f"{'fp32' if es == 4 else 'bf16'} I/O")
-        bytes_fwd, bytes_bwd = es * (2 * C + T), es * 3 * C
-        tags = [4, 5]
-        dtype = "f32"          # arithmetic is fp32 in registers; I/O dtype is in config
-
-    def capture(step):
-        """CUDA-graph capture of one whole step (single process only); None if capture is not possible"""
-        if world > 1 or args.no_graph:
-            return None
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                step()
-            torch.cuda.synchronize()
-            return g
-        except Exception as e:                     # pragma: no cover
-            sys.stderr.write(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); timing eagerly\n")
-            torch.cuda.synchronize()
-            return None
-
-    def timed(run):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
+    def timed(self, run, steps):
+        """CUDA events around each of `steps` runs (L2 flushed between them, outside the events), barrier +
+        synchronize on both sides, max over ranks; seconds per step"""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
         for a, b in ev:
-            l2_flush()                            # L2 flush between timed iterations (outside the events)
+            self.l2_flush()
             a.record()
             run()
             b.record()
-        barrier()
-        sec = sum(a.elapsed_time(b) for a, b in ev) / 1e3 / args.steps
-        t = torch.tensor([sec], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self.barrier()
+        sec = sum(a.elapsed_time(b) for a, b in ev) / 1e3 / steps
+        t = torch.tensor([sec], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- per-kernel durations: eager profiling pass (CUDA events recorded by the library) -------
-    ts = make_dev()
-    for _ in range(args.warmup):
-        step_dev(ts)
-    barrier()
-    prof_steps = min(args.steps, 5)
-    lib.agb_prof_enable(1)
-    n0 = lib.agb_launch_count()
-    for _ in range(prof_steps):
-        l2_flush()
-        step_dev(ts)
-    barrier()
-    launches_per_step = (lib.agb_launch_count() - n0) // prof_steps
-    prof = {t: prof_read(lib, t) for t in tags}
-    lib.agb_prof_enable(0)
+    def graphed(self, fn):
+        if self.world > 1 or self.args.no_graph:
+            return None
+        from attention_gan_b200.agb_native.graph import try_graphed
+        return try_graphed(fn)
 
-    # ---- device-resident timing (the step replayed from a CUDA graph when possible) -------------
-    graph = capture(lambda: step_dev(ts))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    sec = timed(graph.replay if graph is not None else (lambda: step_dev(ts)))
-    clocks = sampler.stop() if rank == 0 else None
-    launches = launches_per_step * args.steps
+    def prof_read(self, tag):
+        ms, n = ctypes.c_double(0.0), ctypes.c_longlong(0)
+        self.lib.agb_prof_read(tag, ctypes.byref(ms), ctypes.byref(n))
+        return ms.value, n.value
 
-    # ---- end to end through the public API with host buffers -----------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    graph2 = capture(step_e2e)
-    sec2 = timed(graph2.replay if graph2 is not None else step_e2e)
+    def measure(self, make_dev, step_dev, step_e2e, tags, steps, warmup, sample_clocks=False):
+        """the four timings of one workload + the per-kernel profile; all ranks call this together"""
+        lib = self.lib
+        ts = make_dev()
+        for _ in range(warmup):
+            step_dev(ts)
+        self.barrier()
+        prof_steps = min(steps, 5)
+        lib.agb_prof_enable(1)
+        n0 = lib.agb_launch_count()
+        for _ in range(prof_steps):
+            self.l2_flush()
+            step_dev(ts)
+        self.barrier()
+        launches_per_step = (lib.agb_launch_count() - n0) // prof_steps
+        prof = {t: self.prof_read(t) for t in tags}
+        lib.agb_prof_enable(0)
+        self.torch.cuda.empty_cache()
+        out = {"prof": prof, "prof_steps": prof_steps, "launches_per_step": int(launches_per_step)}
+        torch = self.torch
+        sampler = ClockSampler(self.local) if (sample_clocks and self.rank == 0) else None
+        g = self.graphed(lambda: step_dev(ts))
+        if g is None and sampler:
+            sampler.start()                       # no graph (torchrun / --no-graph): the eager timing IS the value
+        out["eager"] = self.timed(lambda: step_dev(ts), steps)
+        if g is not None:
+            if sampler:
+                sampler.start()
+            out["value"] = self.timed(g.replay, steps)
+        else:
+            out["value"] = out["eager"]
+        out["clocks"] = sampler.stop() if sampler else None
+        out["graph"] = g is not None
+        del g
+        torch.cuda.empty_cache()                  # a captured step owns a private copy of the workspace
+        for _ in range(max(1, warmup // 2)):
+            step_e2e()
+        self.barrier()
+        out["e2e_eager"] = self.timed(step_e2e, steps)
+        g2 = self.graphed(step_e2e)
+        out["e2e"] = self.timed(g2.replay, steps) if g2 is not None else out["e2e_eager"]
+        out["e2e_graph"] = g2 is not None
+        del g2, ts
+        torch.cuda.empty_cache()
+        return out
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+
+def damsm_workload(env: Env, wl, Bg, math, steps, warmup, sample_clocks):
+    torch, pkg, dev, world, rank = env.torch, env.pkg, env.dev, env.world, env.rank
+    assert Bg % world == 0
+    Bl = Bg // world
+    sl = slice(rank * Bl, rank * Bl + Bl)
+    img, wrd, cnn, rnn, lens, cls = damsm_inputs(Bg)         # every rank: the same global batch, keeps its shard
+    mean_len = float(lens.float().mean())
+    img_h, wrd_h = img[sl].contiguous().pin_memory(), wrd[sl].contiguous().pin_memory()
+    cnn_h, rnn_h = cnn[sl].contiguous().pin_memory(), rnn[sl].contiguous().pin_memory()
+    lens_h = lens[sl].to(torch.int32).contiguous().pin_memory()
+    cls_h = cls[sl].to(torch.int32).contiguous().pin_memory()
+    del img, wrd, cnn, rnn
+    labels = torch.arange(Bl, device=dev)
+    loss_mod = pkg.DAMSMLoss(dev, math=math, process_group=env.group, att_maps="packed", max_words=T_)
+    out_h = torch.empty(2, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (img_h, wrd_h, cnn_h, rnn_h, lens_h, cls_h))
+
+    def make_dev():
+        ts = [img_h.to(dev), wrd_h.to(dev), cnn_h.to(dev), rnn_h.to(dev)]
+        for t in ts:
+            t.requires_grad_(True)
+        return ts + [lens_h.to(dev), cls_h.to(dev)]
+
+    def step_dev(ts):
+        im, wd, cn, rn, ln, cl = ts
+        for t in (im, wd, cn, rn):
+            t.grad = None
+        wl_, sl_, _ = loss_mod.get_losses(im, cn, wd.transpose(1, 2), rn, labels, ln, cl)
+        (wl_ + sl_).backward()
+        return wl_, sl_
+
+    def step_e2e():
+        im = img_h.to(dev, non_blocking=True).requires_grad_(True)
+        wd = wrd_h.to(dev, non_blocking=True).requires_grad_(True)
+        cn = cnn_h.to(dev, non_blocking=True).requires_grad_(True)
+        rn = rnn_h.to(dev, non_blocking=True).requires_grad_(True)
+        ln = lens_h.to(dev, non_blocking=True)
+        cl = cls_h.to(dev, non_blocking=True)
+        wl_, sl_, _ = loss_mod.get_losses(im, cn, wd.transpose(1, 2), rn, labels, ln, cl)
+        (wl_ + sl_).backward()
+        out_h[0:1].copy_(wl_.detach().reshape(1), non_blocking=True)
+        out_h[1:2].copy_(sl_.detach().reshape(1), non_blocking=True)
+
+    tc = math != "fp32"
+    tags = list(DAMSM_KERNELS) if tc else [1]
+    m = env.measure(make_dev, step_dev, step_e2e, tags, steps, warmup, sample_clocks)
+    m.update(units=Bl * Bg, total_units=Bg * Bg, h2d=int(h2d), d2h=8, mean_len=mean_len, tc=tc,
+             flop_unit=2.0 * R_ * mean_len * D_, metric=METRIC_DAMSM, unit="pairs/s",
+             dtype={"fp32": "f32", "f16": "f16", "bf16": "bf16"}[math], math=math)
+    return m
+
+
+def attn_workload(env: Env, wl, batch, hw_only, steps, warmup, sample_clocks, local_share=False):
+    torch, pkg, dev, world, rank = env.torch, env.pkg, env.dev, env.world, env.rank
+    from oracle import ref_port as rp          # seeded input generators only (never inside a timed region)
+    if wl == "cfg1":
+        B, C, E, T, hws, tdt = 16, 32, 256, 18, [64], torch.float32
+    elif wl == "cfg5":
+        B, C, E, T, hws, tdt = 256, 32, 256, 64, [256], torch.bfloat16
+    else:
+        B, C, E, T, hws, tdt = 64, 32, 256, 18, [64, 128, 256], torch.bfloat16
+    if hw_only:
+        hws = [hw_only]
+    B = batch or B
+    if local_share:                              # one GPU's share of an 8-GPU workload, measured on this GPU alone
+        B = B // 8
+        share, rk = 1, 0
+    else:
+        share, rk = world, rank
+    assert B % share == 0
+    Bl = B // share
+    sl = slice(rk * Bl, rk * Bl + Bl)
+    g = torch.Generator().manual_seed(1)
+    img_h, dctx_h = [], []
+    for hw in hws:
+        images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed=0)
+        img_h.append(images[sl].to(tdt).contiguous().pin_memory())
+        dctx_h.append(torch.randn(B, C, hw, hw, generator=g)[sl].to(tdt).contiguous().pin_memory())
+        del images
+    wrd_h = words[sl].transpose(1, 2).contiguous().pin_memory()        # physical [B,T,E]
+    mask_d = mask[sl].to(dev)
+    mods = []
+    for hw in hws:                                                      # one AttentionModule per stage
+        mod = pkg.AttentionModule(C, E).to(dev)
+        with torch.no_grad():
+            mod.conv1.weight.copy_(weight.to(dev))
+        mod.apply_mask(mask_d)
+        mods.append(mod)
+    out_h = torch.empty(256 * len(hws), dtype=tdt).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (*img_h, *dctx_h, wrd_h))
+    d2h = out_h.numel() * out_h.element_size()
+
+    def make_dev():
+        return [[t.to(dev).requires_grad_(True) for t in img_h], wrd_h.to(dev).requires_grad_(True),
+                [t.to(dev) for t in dctx_h]]
+
+    def step_dev(ts):
+        ims, wd, dctxs = ts
+        wd.grad = None
+        outs = []
+        for mod, im, dctx in zip(mods, ims, dctxs):
+            im.grad = None
+            mod.conv1.weight.grad = None
+            ctx, attn = mod(im, wd.transpose(1, 2))
+            ctx.backward(dctx)
+            outs.append((ctx, attn))
+        return outs
+
+    def step_e2e():
+        wd = wrd_h.to(dev, non_blocking=True).requires_grad_(True)
+        for i, (mod, im_h, dc_h) in enumerate(zip(mods, img_h, dctx_h)):
+            im = im_h.to(dev, non_blocking=True).requires_grad_(True)
+            dctx = dc_h.to(dev, non_blocking=True)
+            mod.conv1.weight.grad = None
+            ctx, attn = mod(im, wd.transpose(1, 2))
+            ctx.backward(dctx)
+            out_h[256 * i:256 * (i + 1)].copy_(im.grad.reshape(-1)[:256], non_blocking=True)   # a slice of every stage's result
+
+    npix = sum(hw * hw for hw in hws)
+    es = 4 if tdt == torch.float32 else 2
+    m = env.measure(make_dev, step_dev, step_e2e, [4, 5], steps, warmup, sample_clocks)
+    m.update(units=Bl * npix, total_units=B * npix, h2d=int(h2d), d2h=int(d2h), metric=METRIC_ATTN, unit="pixels/s",
+             bytes_fwd=es * (2 * C + T), bytes_bwd=es * 3 * C, dtype="f32" if es == 4 else "bf16",
+             io="fp32" if es == 4 else "bf16", B=B, T=T, C=C, hws=hws)
+    return m
+
+
+def damsm_roofline(m, peaks, long_step):
+    """per-kernel tensor roofline of one DAMSM measurement (no sums over concurrently running kernels)"""
+    pairs = m["units"] * m["prof_steps"]
+    peak = peaks["tf_sust"] if long_step else peaks["tf_burst"]
+    which = "sustained" if long_step else "burst"
+    kernels = []
+    if m["tc"]:
+        for tag, (name, gemm_units) in DAMSM_KERNELS.items():
+            ms, n = m["prof"][tag]
+            if n == 0:
+                continue
+            tf = gemm_units * m["flop_unit"] * pairs / (ms * 1e-3) / 1e12
+            kernels.append({"kernel": name, "launches": int(n), "avg_launch_ms": ms / n, "ms_per_step": ms / m["prof_steps"],
+                            "algorithmic_gemm_units_per_pair": gemm_units, "achieved": tf, "frac": tf / peak})
+    else:
+        ms, n = m["prof"][1]
+        tf = 6 * m["flop_unit"] * pairs / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        kernels.append({"kernel": "sgemm_strided_kernel (fp32 CUDA cores)", "launches": int(n),
+                        "avg_launch_ms": ms / max(n, 1), "ms_per_step": ms / m["prof_steps"],
+                        "algorithmic_gemm_units_per_pair": 6, "achieved": tf, "frac": tf / peak})
+    dom = max(kernels, key=lambda k: k["ms_per_step"])
+    step_tf = 6 * m["flop_unit"] * m["units"] / m["value"] / 1e12
+    roof = {"bound": "tensor", "achieved": dom["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": dom["frac"],
+            "traffic": load_traffic("damsm_bwd3_kernel") if ("bwd3" in dom["kernel"]) else None,
+            "kernel": dom["kernel"], "launches": dom["launches"], "avg_launch_ms": dom["avg_launch_ms"],
+            "peak_source": f"{peaks['source']} dense bf16 {which} (kernel timed with CUDA events on its launching stream "
+                           f"inside {'a long step' if long_step else 'a short step'})",
+            "algorithmic": "GEMM unit = 2*R*mean(cap_len)*D flop per (image,caption) pair; fwd 2 units, d beta 1, "
+                           "d img 2, d words 1 = 12*R*L*D per pair (recomputation is not counted)",
+            "step": {"achieved": step_tf, "frac": step_tf / peak, "frac_of_burst": step_tf / peaks["tf_burst"],
+                     "note": "all 12*R*L*D flop per pair of this rank / device-timed step"},
+            "kernels": kernels}
+    return roof
+
+
+def attn_roofline(m, peaks):
+    (ms_f, n_f), (ms_b, n_b) = m["prof"][4], m["prof"][5]
+    px = m["units"] * m["prof_steps"]
+    fwd = m["bytes_fwd"] * px / 1e9 / (ms_f * 1e-3) if ms_f > 0 else 0.0
+    bwd = m["bytes_bwd"] * px / 1e9 / (ms_b * 1e-3) if ms_b > 0 else 0.0
+    both = (m["bytes_fwd"] + m["bytes_bwd"]) * px / 1e9 / ((ms_f + ms_b) * 1e-3) if ms_f + ms_b > 0 else 0.0
+    step = (m["bytes_fwd"] + m["bytes_bwd"]) * m["units"] / 1e9 / m["value"]
+    dom_bwd = ms_b >= ms_f
+    return {"bound": "hbm", "achieved": bwd if dom_bwd else fwd, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": (bwd if dom_bwd else fwd) / peaks["hbm"], "traffic": None,
+            "kernel": "word_attn_bwd_tc_kernel" if dom_bwd else "word_attn_fwd_tc_kernel",
+            "launches": int(n_b if dom_bwd else n_f), "avg_launch_ms": (ms_b / max(n_b, 1)) if dom_bwd else (ms_f / max(n_f, 1)),
+            "fwd_gbs": fwd, "bwd_gbs": bwd, "fwd_bwd_kernels_gbs": both, "fwd_bwd_kernels_frac": both / peaks["hbm"],
+            "step": {"achieved": step, "frac": step / peaks["hbm"],
+                     "note": "algorithmic bytes of all stages / device-timed step (projection + reduction kernels included)"},
+            "peak_source": f"{peaks['source']} HBM copy", "algorithmic": "es*(2C+T) B/pixel fwd + es*3C B/pixel bwd"}
+
+
+def summary(m, roof, name):
+    """compact record of a secondary workload"""
+    return {"workload": name, "metric": m["metric"], "unit": m["unit"], "value": m["total_units"] / m["value"],
+            "ms_per_step": m["value"] * 1e3, "eager_ms_per_step": m["eager"] * 1e3,
+            "e2e": {"value": m["total_units"] / m["e2e"], "ms_per_step": m["e2e"] * 1e3,
+                    "eager_ms_per_step": m["e2e_eager"] * 1e3, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+            "cuda_graph": m["graph"], "gpu_launches_per_step": m["launches_per_step"], "dtype": m["dtype"], "roofline": roof}
+
+
+def run_native(args):
+    env = Env(args)
+    torch = env.torch
+    peaks = load_peaks()
+    wl = args.workload
+    damsm = wl in ("cfg2", "cfg4")
+    if damsm:
+        Bg = args.batch or CFG_BATCH[wl]
+        m = damsm_workload(env, wl, Bg, args.math, args.steps, args.warmup, True)
+        roof = damsm_roofline(m, peaks, long_step=m["value"] > 2e-3)
+        name = workload_name(wl, Bg)
+    else:
+        m = attn_workload(env, wl, args.batch, args.hw, args.steps, args.warmup, True)
+        roof = attn_roofline(m, peaks)
+        name = workload_name(wl)
+
+    secondary = {}
+    if env.world == 1 and args.secondary and not (args.batch or args.hw):
+        ssteps, swarm = min(args.steps, 20), 3
+        for w2 in ("cfg2", "cfg3", "cfg5"):
+            if w2 == wl:
+                continue
+            try:
+                if w2 == "cfg2":
+                    m2 = damsm_workload(env, w2, CFG_BATCH[w2], args.math, ssteps, swarm, False)
+                    secondary[w2] = summary(m2, damsm_roofline(m2, peaks, long_step=False), workload_name(w2))
+                else:
+                    m2 = attn_workload(env, w2, None, None, ssteps, swarm, False, local_share=(w2 == "cfg5"))
+                    nm = workload_name(w2) + ("; ONE GPU's share (32 samples) measured on this GPU" if w2 == "cfg5" else "")
+                    secondary[w2] = summary(m2, attn_roofline(m2, peaks), nm)
+            except Exception as e:                 # a failing secondary must not take the headline down with it
+                secondary[w2] = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.synchronize()
+
+    if env.rank != 0:
+        if env.world > 1:
+            env.dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------
-    if damsm:
-        ms_tot = sum(prof[t][0] for t in tags)
-        n_l = sum(prof[t][1] for t in tags)
-        flops = flop_per_unit * units * prof_steps            # algorithmic flops the profiled launches covered
-        ach = flops / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
-        peak = peaks["tf_burst"]
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": load_traffic(args.workload) if (tc and args.batch is None) else None,
-                "kernel": "damsm_fwd2_kernel + damsm_bwd3_kernel + tc_gemm_kernel (tcgen05)" if tc else "sgemm_strided_kernel (fp32 CUDA cores)",
-                "launches": int(n_l), "avg_launch_ms": ms_tot / max(n_l, 1),
-                "peak_source": f"{peaks['source']} bf16 burst (kernels timed one by one with events)",
-                "algorithmic": "12*R*mean(cap_len)*D flop per (image,caption) pair, fwd+bwd"}
-    else:
-        (ms_f, n_f), (ms_b, n_b) = prof[4], prof[5]
-        gb = (bytes_fwd + bytes_bwd) * units * prof_steps / 1e9
-        ach = gb / ((ms_f + ms_b) * 1e-3) if ms_f + ms_b > 0 else 0.0
-        roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                "traffic": load_traffic(args.workload) if (args.batch is None and args.hw is None) else None,
-                "kernel": "word_attn_fwd(_tc)_kernel + word_attn_bwd(_tc)_kernel",
-                "launches": int(n_f + n_b), "avg_launch_ms": (ms_f + ms_b) / max(n_f + n_b, 1),
-                "fwd_gbs": bytes_fwd * units * prof_steps / 1e9 / (ms_f * 1e-3) if ms_f > 0 else None,
-                "bwd_gbs": bytes_bwd * units * prof_steps / 1e9 / (ms_b * 1e-3) if ms_b > 0 else None,
-                "peak_source": f"{peaks['source']} HBM copy",
-                "algorithmic": "es*(2C+T) B/pixel fwd + es*3C B/pixel bwd"}
+    # ---- baselines on this box (rank 0, N=1 only): the oracle port on the host cores and on the GPU (torch eager) ----
+    cpu = gpu_eager = None
+    if env.world == 1:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        if damsm:
+            cstep, cunits = ref_damsm_step(48, CFG_BATCH["cfg4"] if wl == "cfg4" else 48)
+            csample = ("oracle/ref_port.py WordsLoss+SentenceLoss fwd+bwd on the first 48 samples of the workload's batch "
+                       "(48x48 pairs per step), fp32, 3 steps after 1 warm-up")
+            gstep, gunits = ref_damsm_step(128, max(128, CFG_BATCH.get(wl, 128)), device=env.dev)
+            gsample = "oracle/ref_port.py (torch eager: ATen + cuBLAS) on cuda:0, first 128 samples (128x128 pairs), fp32"
+        else:
+            cstep, cunits = ref_attn_step(16, 32, 256, 18, 64)
+            csample = "oracle/ref_port.py word_attention fwd+bwd at B=16, 64x64 (cfg1 shape), fp32, 3 steps after 1 warm-up"
+            gstep, gunits = ref_attn_step(16, 32, 256, 18, 128, device=env.dev)
+            gsample = "oracle/ref_port.py word_attention (torch eager) on cuda:0, B=16, 128x128, fp32"
+        csec = time_host(cstep, 3, 1)
+        cpu = {"value": cunits / csec, "unit": m["unit"], "cores": torch.get_num_threads(), "kind": "port", "sample": csample}
+        try:
+            gsec = time_host(gstep, 5, 2, sync=torch.cuda.synchronize)
+            gpu_eager = {"value": gunits / gsec, "unit": m["unit"], "sample": gsample,
+                         "note": "per-unit rate of the reference's own op sequence on this B200; not the product"}
+        except Exception as e:
+            gpu_eager = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) -----------------
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    if damsm:
-        cstep, cunits = cpu_damsm_step(48)
-        csample = "oracle/ref_port.py WordsLoss+SentenceLoss fwd+bwd at B=48 (cfg2 shape), fp32, 3 steps after 1 warm-up"
-    else:
-        cstep, cunits = cpu_attn_step(16, 32, 256, 18, 64)
-        csample = "oracle/ref_port.py word_attention fwd+bwd at B=16, 64x64 (cfg1 shape), fp32, 3 steps after 1 warm-up"
-    csec = time_cpu(cstep, 3, 1)
-    cpu = {"value": cunits / csec, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": csample}
-
-    line = {"metric": metric, "value": total_units / sec, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None, "dtype": dtype,
-            "data": "synthetic",
-            "config": {"workload": workload, "l2": "256 MiB L2 flush between timed iterations",
-                       "timing": "CUDA events per step on the current stream, max over ranks",
-                       "cuda_graph": {"value": graph is not None, "e2e": graph2 is not None},
-                       "roofline_timing": f"library CUDA events around the dominant kernels in an eager pass of "
-                                          f"{prof_steps} steps before the timed region"},
-            "e2e": {"value": total_units / sec2, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-                    "ms_per_step": sec2 * 1e3},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+    sec, sec2 = m["value"], m["e2e"]
+    line = {"metric": m["metric"], "value": m["total_units"] / sec, "unit": m["unit"], "n_gpus": env.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong" if wl in ("cfg4", "cfg5") else "weak", "vs_baseline": None, "dtype": m["dtype"],
+            "data": "synthetic", "config": {"workload": name},
+            "method": {"math": args.math if damsm else None,
+                       "l2": "256 MiB write between timed iterations (outside the events)",
+                       "timing": "CUDA events per step on the current stream, barrier + synchronize on both sides, max over ranks",
+                       "cuda_graph": {"value": m["graph"], "e2e": m["e2e_graph"]},
+                       "sharding": ("rows [k*B/N,(k+1)*B/N) per rank, NCCL all-gather of word features + similarity blocks, "
+                                    "reduce-scatter of d words" if env.world > 1 and damsm else
+                                    ("batch split over the ranks, no collective" if env.world > 1 else "single process")),
+                       "roofline_timing": f"library CUDA events around each kernel in an eager pass of {m['prof_steps']} steps"},
+            "eager": {"value": m["total_units"] / m["eager"], "ms_per_step": m["eager"] * 1e3},
+            "e2e": {"value": m["total_units"] / sec2, "unit": m["unit"], "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"], "ms_per_step": sec2 * 1e3},
+            "e2e_eager": {"value": m["total_units"] / m["e2e_eager"], "ms_per_step": m["e2e_eager"] * 1e3},
+            "gpu_launches": int(m["launches_per_step"] * args.steps), "gpu_launches_per_step": m["launches_per_step"],
+            "roofline": roof, "cpu_baseline": cpu, "torch_eager_gpu": gpu_eager, "clocks": m["clocks"]}
+    if secondary:
+        line["secondary"] = secondary
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -495,17 +640,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--math", default=None, choices=["fp32", "f16", "bf16"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--hw", type=int, default=None, help="attention workloads: a single feature-map side instead of the config's stages")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="N=1: skip the cfg2 / cfg3 / cfg5 measurements reported under 'secondary'")
     args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload is None:
-        args.workload = "cfg2" if max(world, args.gpus) == 1 else "cfg4"
     if args.impl == "reference":
-        args.warmup = min(args.warmup, 2)    # each CPU step is a bounded sample (0.5-3 s); warm-up is cheap to cap
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
     if args.math is None:

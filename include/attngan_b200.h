@@ -56,11 +56,18 @@ const char* agb_last_error(void);
 /* 1 when the library was built with the tcgen05 (sm_100a) DAMSM kernels */
 int agb_has_tcgen05(void);
 
-/* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional
- * per-kernel timing with CUDA events recorded on the launching stream around the dominant kernels.
- * tag: 1 = fp32 sgemm, 2 = tcgen05 DAMSM forward, 3 = tcgen05 DAMSM backward,
- *      4 = word-attention forward, 5 = word-attention backward (main kernel).
- * agb_prof_read synchronises the recorded events and returns the summed duration and the count. */
+/* Process-wide tuning / test options.  Each is read from the environment ONCE (first use of the library) and can
+ * be overridden here; none changes results, only how the work is staged:
+ *   "damsm_chunk_mb"  (AGB_DAMSM_CHUNK_MB, 16384)  HBM staging budget of one chunk of word tiles in the tensor-core
+ *                     DAMSM backward; a small value forces the multi-chunk path (tests do that)
+ *   "damsm_save_mb"   (AGB_DAMSM_SAVE_MB, 65536)   budget for the context vectors the training forward saves;
+ *                     above it the backward recomputes them (damsm_bwd2_kernel)
+ *   "damsm_bwd"       (AGB_DAMSM_BWD, 0)           2 = always the recomputing backward
+ *   "damsm_uniform_split", "attn_fwd_stages", "attn_fwd_ctas", "attn_bwd_stages", "attn_bwd_ctas": kernel tuning
+ * Set an option BEFORE querying a workspace size that depends on it and keep it unchanged between a forward and its
+ * backward.  Returns 0, or AGB_E_BADARG for an unknown name. */
+int agb_set_option(const char* name, long long value);
+
 /* Self-test of the tcgen05 / TMEM / TMA building blocks: one CTA computes
  * C[128,N] = A[128,K] * B[N,K]^T from 16-bit row-major device buffers (fp32 accumulate in TMEM).
  * K % 64 == 0, K <= 256, N in {128, 256}; manual_a != 0 stages A through the thread-written
@@ -74,6 +81,12 @@ int agb_tc_selftest(const void* A, const void* B, float* C, int N, int K, int bf
 int agb_tc_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mn, int b_mn,
                      int bf16, int accumulate, void* stream);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched so far, and optional
+ * per-kernel timing with CUDA events recorded on the launching stream around the dominant kernels.
+ * tag: 1 = fp32 sgemm, 2 = tcgen05 DAMSM forward pair kernel, 3 = tcgen05 DAMSM backward pair kernel,
+ *      4 = word-attention forward, 5 = word-attention backward (main kernel),
+ *      6 = d img reduction GEMM (tcgen05), 7 = d words reduction GEMM (tcgen05).
+ * agb_prof_read synchronises the recorded events and returns the summed duration and the count. */
 long long agb_launch_count(void);
 void agb_prof_enable(int on);
 int agb_prof_read(int tag, double* total_ms, long long* launches);

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import attention_gan_b200 as pkg
-from agb_native import ops
+from attention_gan_b200.agb_native import ops
 lib = pkg.native.lib()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 g = torch.Generator().manual_seed(0)

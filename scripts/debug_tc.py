@@ -2,7 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import attention_gan_b200 as pkg
-from agb_native import ops
+from attention_gan_b200.agb_native import ops
 from oracle import closed_form as cf, ref_port as rp
 np.set_printoptions(precision=4, linewidth=200, suppress=True)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 7

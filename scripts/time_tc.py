@@ -3,7 +3,7 @@ import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import attention_gan_b200 as pkg
-from agb_native import ops
+from attention_gan_b200.agb_native import ops
 from oracle import ref_port as rp
 lib = pkg.native.lib()
 def read(tag):

@@ -110,3 +110,49 @@ def test_persistent_attention_is_deterministic_and_batch_split_invariant(agb):
         assert torch.equal(x, y)
     c = run(slice(5, 16))
     assert torch.equal(c[0], a[0][5:16]) and torch.equal(c[1], a[1][5:16]) and torch.equal(c[2], a[2][5:16])
+
+
+# ------------------------------------------------------------------------------------------------
+# GenNextStage's concat epilogue -- context written straight into cat((h, ctx), 1)
+# reference: networks/generator_submodules.py:113-116
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,want_attn", [(torch.float32, True), (torch.bfloat16, True), (torch.float16, False)])
+@pytest.mark.parametrize("B,hw,T,C", [(3, 16, 18, 32), (4, 40, 7, 32), (2, 12, 5, 20)])
+def test_forward_into_concat_buffer_matches_cat_of_oracle(agb, dtype, want_attn, B, hw, T, C):
+    E = 64
+    images, words, weight, mask, _ = rp.synth_attention(B, C, E, T, hw, seed=31 * B + hw)
+    images = images.to(dtype)
+    g = torch.Generator().manual_seed(5)
+    dout = torch.randn(B, 2 * C, hw, hw, generator=g).to(dtype)
+    mod = agb.AttentionModule(C, E).cuda()
+    with torch.no_grad():
+        mod.conv1.weight.copy_(weight.cuda())
+    mod.apply_mask(mask.cuda())
+    im = images.cuda().requires_grad_(True)
+    wd = words.cuda().requires_grad_(True)
+    buf = torch.full((B, 2 * C, hw, hw), float("nan"), dtype=dtype, device="cuda")
+    out, attn = mod.forward_into(im, wd, buf, want_attn=want_attn)
+    assert out.data_ptr() == buf.data_ptr() and (attn is None) == (not want_attn)
+    out.backward(dout.cuda())
+
+    h = images.double().numpy().reshape(B, C, -1)
+    W2 = weight.reshape(C, E).double().numpy()
+    rc, ra, _ = cf.word_attention_fwd(h, words.numpy(), W2, mask.numpy(), True)
+    ref_out = np.concatenate([h, rc], axis=1).reshape(B, 2 * C, hw, hw)        # torch.cat((h_code, c_code), 1)
+    d = dout.double().numpy().reshape(B, 2 * C, -1)
+    dh, dwords, dW = cf.word_attention_bwd(h, words.numpy(), W2, mask.numpy(), d[:, C:], None, True)
+    dh = dh + d[:, :C]                                                          # cat backward: identity half
+    tol = 1e-5 if dtype == torch.float32 else 1e-3 + (2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11)
+    assert torch.equal(out[:, :C], im.detach())
+    assert rel_err(out, ref_out) < tol
+    if want_attn:
+        assert rel_err(attn, ra.reshape(B, T, hw, hw)) < tol
+    gtol = 2e-5 if dtype == torch.float32 else tol * 2
+    assert rel_err(im.grad, dh.reshape(im.shape)) < gtol
+    assert rel_err(wd.grad, dwords) < gtol
+    assert rel_err(mod.conv1.weight.grad.reshape(C, E), dW) < gtol
+    # same numbers as the two-step route of the reference (attention, then torch.cat)
+    im2 = images.cuda().requires_grad_(True)
+    ctx2, _ = mod(im2, words.cuda())
+    two_step = torch.cat((im2, ctx2), 1)
+    assert torch.equal(two_step, out)

@@ -1,0 +1,179 @@
+"""GPU parity of the paths the large-batch benchmark (cfg4, global batch 2048) runs through but the
+small fixtures never reach: the multi-chunk staging loop of the tensor-core DAMSM backward
+(csrc/damsm_tc_bwd2_host.inc: `for t0 += ct`, `accumulate = (t0 > 0)`, per-chunk scatter of d words) and the
+fp16 gradient scale at large row blocks (Bi = 256 x Bc = 2048, one rank's share of cfg4 on 8 GPUs).
+
+The chunk budget is a process-wide option of the library (include/attngan_b200.h: agb_set_option); a small
+budget forces >= 3 chunks at B = 64.  References: the fp64 closed-form oracle (pinned to the reference's golden
+vectors by tests/test_oracle_golden.py) and the native fp32 path (itself oracle-pinned at 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+from oracle import ref_port as rp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def agb():
+    import attention_gan_b200 as pkg
+    return pkg
+
+
+@pytest.fixture
+def chunk_budget(agb):
+    """sets the staging budget for one test and restores the default afterwards"""
+    def set_mb(mb):
+        agb.native.set_option("damsm_chunk_mb", mb)
+    yield set_mb
+    agb.native.set_option("damsm_chunk_mb", 16384)
+    agb.native.set_option("damsm_save_mb", 65536)
+    agb.native.set_option("damsm_bwd", 0)
+
+
+def _rel(x, ref):
+    x = x.detach().double().cpu().numpy() if torch.is_tensor(x) else np.asarray(x, np.float64)
+    ref = ref.detach().double().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref, np.float64)
+    return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+def _fwd_bwd(ops, native, img3, wrd, l32, dm, math, need_dwords=True):
+    m, _, _, ws = ops.damsm_fwd(img3, wrd, l32, 4.0, 5.0, 1e-8, 0, False, math, keep_ws=True,
+                                save=math != native.AGB_MATH_FP32)
+    dimg, dwords = ops.damsm_bwd(img3, wrd, l32, 4.0, 5.0, 1e-8, dm, None, need_dwords, math, m,
+                                 ws if math != native.AGB_MATH_FP32 else None, math != native.AGB_MATH_FP32)
+    return m, dimg, dwords
+
+
+@pytest.mark.parametrize("math", ["f16", "bf16"])
+@pytest.mark.parametrize("chunk_mb,min_chunks", [(11, 6), (22, 3), (33, 2)])
+def test_multi_chunk_backward_matches_single_chunk_fp32_and_oracle(agb, chunk_budget, math, chunk_mb, min_chunks):
+    """B = 64 (tile staging = 64*128*1284 B = 10.5 MB per word tile; 11 tiles at most, 6-7 in use):
+    ct = 1 / 2 / 3 tiles per chunk, i.e. >= 6 / 3 / 2 chunks, some of them past the last used tile."""
+    from attention_gan_b200.agb_native import native, ops
+    B = 64
+    mode = native.MATH_NAMES[math]
+    img, wrd, _, _, _, lens, _ = rp.synth_damsm(B, seed=640)
+    lens[:4] = torch.tensor([18, 1, 18, 2])
+    img3 = img.cuda().reshape(B, 256, -1).contiguous()
+    wd = wrd.cuda()
+    l32 = lens.cuda().to(torch.int32)
+    g = torch.Generator().manual_seed(7)
+    dm = (torch.randn(B, B, generator=g) * (1.0 / B)).cuda()
+
+    chunk_budget(16384)                                   # single chunk
+    m1, dimg1, dw1 = _fwd_bwd(ops, native, img3, wd, l32, dm, mode)
+    chunk_budget(chunk_mb)
+    nt_max = (B + 5) // 6
+    tile_mb = B * 128 * (320 * 2 * 2 + 4) / 2 ** 20
+    ct = max(1, int(chunk_mb // tile_mb))
+    assert (nt_max + ct - 1) // ct >= min_chunks, "the budget does not force the intended number of chunks"
+    m2, dimg2, dw2 = _fwd_bwd(ops, native, img3, wd, l32, dm, mode)
+    assert torch.equal(m1, m2)                                             # the forward does not depend on the budget
+    # d img: the chunks accumulate into the same fp32 output in tile order -> only fp32 re-association differs
+    assert _rel(dimg2, dimg1) < 2e-6, _rel(dimg2, dimg1)
+    # d words: every word row belongs to exactly one tile, hence to one chunk
+    assert _rel(dw2, dw1) < 2e-6, _rel(dw2, dw1)
+
+    # against the oracle-pinned fp32 path and the fp64 oracle
+    _, dimg32, dw32 = _fwd_bwd(ops, native, img3, wd, l32, dm, native.AGB_MATH_FP32)
+    gtol = 5e-3 if math == "f16" else 2e-2
+    assert _rel(dimg2, dimg32) < gtol and _rel(dw2, dw32) < gtol
+    dc0, dw0 = cf.words_similarity_bwd(img.numpy().reshape(B, 256, -1), wrd.numpy(), lens.numpy(), dm.cpu().numpy())
+    assert _rel(dimg2, dc0) < gtol
+    assert _rel(dw2.transpose(1, 2), dw0) < gtol
+    assert _rel(dimg32, dc0) < 1e-4 and _rel(dw32.transpose(1, 2), dw0) < 1e-4
+
+
+def test_multi_chunk_through_the_drop_in_loss(agb, chunk_budget):
+    """the same forced chunking through WordsLoss (loss, class-id mask, autograd glue), frozen and trainable words"""
+    B = 64
+    img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, seed=641, n_classes=16)
+    wl0, _, dc0, dw0 = cf.words_loss_fwd_bwd(img.numpy().reshape(B, 256, -1), wrd.numpy(), labels.numpy(),
+                                             lens.numpy(), cls)
+    chunk_budget(11)
+    im = img.cuda().requires_grad_(True)
+    wd = wrd.cuda().requires_grad_(True)
+    wl, _ = agb.WordsLoss("cuda", math="f16").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
+    assert abs(wl.item() - wl0) <= 1e-4 * abs(wl0), (wl.item(), wl0)
+    wl.backward()
+    assert _rel(im.grad, dc0.reshape(img.shape)) < 5e-3
+    assert _rel(wd.grad, dw0) < 5e-3
+    im2 = img.cuda().requires_grad_(True)
+    wl2, _ = agb.WordsLoss("cuda", math="f16").get_loss(im2, wrd.cuda(), labels.cuda(), lens.cuda(), cls)
+    wl2.backward()
+    assert _rel(im2.grad, dc0.reshape(img.shape)) < 5e-3
+
+
+def test_multi_chunk_recomputing_backward(agb, chunk_budget):
+    """the recomputing backward (damsm_bwd2_kernel: taken when the saved vectors exceed the save budget) through
+    the same chunk loop; selected here by a zero save budget"""
+    from attention_gan_b200.agb_native import native, ops
+    B = 48
+    img, wrd, _, _, _, lens, _ = rp.synth_damsm(B, seed=642)
+    img3 = img.cuda().reshape(B, 256, -1).contiguous()
+    wd = wrd.cuda()
+    l32 = lens.cuda().to(torch.int32)
+    dm = (torch.randn(B, B, generator=torch.Generator().manual_seed(8)) * (1.0 / B)).cuda()
+    dc0, dw0 = cf.words_similarity_bwd(img.numpy().reshape(B, 256, -1), wrd.numpy(), lens.numpy(), dm.cpu().numpy())
+    agb.native.set_option("damsm_save_mb", 0)
+    chunk_budget(25)                                       # staging incl. dV16: 48*128*1796 B = 10.5 MB per tile
+    _, dimg, dw = _fwd_bwd(ops, native, img3, wd, l32, dm, native.AGB_MATH_TC_F16)
+    assert _rel(dimg, dc0) < 5e-3 and _rel(dw.transpose(1, 2), dw0) < 5e-3
+
+
+def test_large_row_block_f16_against_fp32_path(agb):
+    """one rank's share of cfg4 on 8 GPUs: Bi = 256 images x Bc = 2048 captions.  Covers the fp16 gradient scale
+    sg = 2^e >= 64*Bi at large Bi, d words summed over 256 images (16 K-slices), and m at 524k pairs, against the
+    native fp32 path (oracle-pinned at 1e-5 by tests/test_gpu_parity.py)."""
+    from attention_gan_b200.agb_native import native, ops
+    Bi, Bc, r0 = 256, 2048, 512
+    g = torch.Generator().manual_seed(2048)
+    img3 = torch.randn(Bi, 256, 289, generator=g).cuda()
+    wd = torch.randn(Bc, 18, 256, generator=g).cuda().transpose(1, 2)          # the RNN's transposed view
+    lens = torch.randint(2, 19, (Bc,), generator=g)
+    lens[0] = 18
+    l32 = lens.cuda().to(torch.int32)
+    # dLoss/dm of a realistic two-way CE: O(1/B) on the diagonal block, tiny elsewhere
+    dm = torch.randn(Bi, Bc, generator=g) * (0.05 / Bc)
+    dm[torch.arange(Bi), r0 + torch.arange(Bi)] -= 50.0 / Bc
+    dm = dm.cuda()
+    out = {}
+    for name, mode in (("f16", native.AGB_MATH_TC_F16), ("fp32", native.AGB_MATH_FP32)):
+        m, _, _, ws = ops.damsm_fwd(img3, wd, l32, 4.0, 5.0, 1e-8, r0, False, mode, keep_ws=True, save=mode != 0)
+        dimg, dwords = ops.damsm_bwd(img3, wd, l32, 4.0, 5.0, 1e-8, dm, None, True, mode, m, ws if mode else None,
+                                     mode != 0)
+        out[name] = (m, dimg, dwords)
+        del ws
+    assert (out["f16"][0] - out["fp32"][0]).abs().max().item() < 2e-3
+    assert _rel(out["f16"][1], out["fp32"][1]) < 5e-3
+    assert _rel(out["f16"][2], out["fp32"][2]) < 5e-3
+    # spot-check rows of the fp32 reference itself against the fp64 oracle (8 images x 64 captions)
+    sub_c = img3[:8].cpu().numpy()
+    sub_w = wd[:64].cpu().numpy()
+    ref = cf.words_similarity_fwd(sub_c, sub_w, lens[:64].numpy())
+    assert np.abs(out["fp32"][0][:8, :64].double().cpu().numpy() - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("B", [256])
+def test_f16_loss_within_1e4_of_fp32_path_at_large_batch(agb, B):
+    """north_star's loss tolerance (1e-4 relative) for the benchmarked math mode at a batch the fp64 oracle cannot
+    reach in seconds: f16 loss vs the native fp32 path, plus gradients"""
+    img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, seed=2560, n_classes=64)
+    res = {}
+    for math in ("fp32", "f16"):
+        im = img.cuda().requires_grad_(True)
+        wd = wrd.cuda().requires_grad_(True)
+        cn = cnn.cuda().requires_grad_(True)
+        rn = rnn.cuda().requires_grad_(True)
+        wl, sl, _ = agb.DAMSMLoss("cuda", math=math, att_maps=None).get_losses(im, cn, wd, rn, labels.cuda(),
+                                                                              lens.cuda(), cls)
+        (wl + sl).backward()
+        res[math] = (wl.item(), sl.item(), im.grad, wd.grad, cn.grad, rn.grad)
+    assert abs(res["f16"][0] - res["fp32"][0]) <= 1e-4 * abs(res["fp32"][0]), (res["f16"][0], res["fp32"][0])
+    assert abs(res["f16"][1] - res["fp32"][1]) <= 1e-5 * abs(res["fp32"][1])
+    assert _rel(res["f16"][2], res["fp32"][2]) < 5e-3
+    assert _rel(res["f16"][3], res["fp32"][3]) < 5e-3
+    assert _rel(res["f16"][4], res["fp32"][4]) < 1e-4 and _rel(res["f16"][5], res["fp32"][5]) < 1e-4

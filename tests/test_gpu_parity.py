@@ -316,7 +316,7 @@ def test_damsm_frozen_text_encoder_skips_dwords(agb):
 def test_damsm_row_blocks_equal_full_matrix(agb):
     """the sharding identity at cfg2 size: row blocks computed with row_offset reproduce the full
     similarity matrix and the matched-pair attention maps bit for bit"""
-    from agb_native import ops
+    from attention_gan_b200.agb_native import ops
     B = 48
     img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, seed=0)
     img3 = img.cuda().reshape(B, 256, -1).contiguous()
@@ -339,7 +339,7 @@ def test_damsm_row_blocks_equal_full_matrix(agb):
 
 
 def test_contrastive_matches_oracle(agb):
-    from agb_native import ops
+    from attention_gan_b200.agb_native import ops
     rng = np.random.default_rng(0)
     B = 37
     raw = rng.normal(size=(B, B)).astype(np.float32)
@@ -378,7 +378,7 @@ def test_damsm_edge_cases(agb):
 
 
 def test_native_rejects_unsupported_shapes(agb):
-    from agb_native import native, ops
+    from attention_gan_b200.agb_native import native, ops
     with pytest.raises(native.NativeError):
         ops.damsm_fwd(torch.zeros(1, 32, 9, device="cuda"), torch.zeros(1, 32, 65, device="cuda"),
                       torch.ones(1, dtype=torch.int32, device="cuda"), 4.0, 5.0)

@@ -96,7 +96,7 @@ def _rel(x, ref):
 @pytest.mark.parametrize("B,full,trained", [(7, True, False), (16, False, False), (48, False, 0.12), (130, False, False)])
 def test_tc_similarity_matrix_matches_oracle(agb, math, tol, B, full, trained):
     """m[b,i] = log sum_t exp(gamma2 cos) for every pair, against the fp64 closed form"""
-    from agb_native import native, ops
+    from attention_gan_b200.agb_native import native, ops
     img, wrd, _, _, _, lens, _ = rp.synth_damsm(B, seed=200 + B, full_len=full, trained_like=trained)
     img3 = img.cuda().reshape(B, 256, -1).contiguous()
     m, att, _ = ops.damsm_fwd(img3, wrd.cuda(), lens.cuda().to(torch.int32), 4.0, 5.0, 1e-8, 0, True,
@@ -157,7 +157,7 @@ def test_tc_words_loss_cfg2(agb, math):
 
 def test_tc_row_blocks_and_ragged_lengths(agb):
     """sharding identity + extreme caption lengths (1 and T) + L = 0 guard"""
-    from agb_native import ops
+    from attention_gan_b200.agb_native import ops
     B = 40
     img, wrd, _, _, _, lens, _ = rp.synth_damsm(B, seed=5)
     lens[:8] = torch.tensor([1, 18, 1, 1, 18, 2, 17, 1])
@@ -190,7 +190,7 @@ def test_tc_other_region_counts_and_lengths(agb, hw, T, B):
 
 def test_tc_rectangular_block_with_row_offset_and_upstream_scale(agb):
     """Bi != Bc (a rank's row block), explicit upstream gradient scale, frozen words (no dwords)"""
-    from agb_native import native, ops
+    from attention_gan_b200.agb_native import native, ops
     B, Bi, r0 = 24, 8, 8
     img, wrd, _, _, _, lens, _ = rp.synth_damsm(B, seed=77)
     c = img.numpy().reshape(B, 256, -1)[r0:r0 + Bi]
@@ -212,7 +212,7 @@ def test_tc_rectangular_block_with_row_offset_and_upstream_scale(agb):
 
 
 def test_tc_unsupported_shapes_fail_loudly(agb):
-    from agb_native import native, ops
+    from attention_gan_b200.agb_native import native, ops
     assert not ops.damsm_supported(33, 256, 289, native.AGB_MATH_TC_F16)       # T > 32
     assert not ops.damsm_supported(18, 128, 289, native.AGB_MATH_TC_F16)       # D != 256
     assert not ops.damsm_supported(18, 256, 361, native.AGB_MATH_TC_F16)       # R > 320

@@ -64,11 +64,76 @@ def test_dropin_interface_matches_reference_signatures():
     assert list(inspect.signature(sl.get_loss).parameters) == ["cnn_code", "rnn_code", "labels", "class_ids", "eps"]
     x1, x2 = torch.randn(5, 7), torch.randn(5, 7)
     torch.testing.assert_close(wl.cosine_similarity(x1, x2), torch.nn.functional.cosine_similarity(x1, x2))
-    # reference top-level import paths resolve to the drop-ins
-    from networks.attention import AttentionModule
-    from losses.words_loss import WordsLoss
-    from losses.sentence_loss import SentenceLoss
-    assert AttentionModule is pkg.AttentionModule and WordsLoss is pkg.WordsLoss and SentenceLoss is pkg.SentenceLoss
+    # importing the package does not shadow the reference's top-level packages
+    assert not any(p.rstrip("/").endswith("attention-gan_b200") for p in sys.path)
+
+
+_INSTALL_CHILD = r'''
+import os, sys
+ref = sys.argv[1]
+order = sys.argv[2]
+sys.path.insert(0, ref)
+sys.path.insert(0, sys.argv[3])
+if order == "after":                      # the reference's modules are imported first, install() rebinds them
+    import networks.generator_submodules as gs
+    import losses.words_loss as ref_wl
+    from losses.words_loss import WordsLoss as RefWordsLoss
+import attention_gan_b200 as agb
+agb.install()
+from networks.attention import AttentionModule, func_attention
+from losses.words_loss import WordsLoss
+from losses.sentence_loss import SentenceLoss
+assert AttentionModule is agb.AttentionModule and func_attention is agb.func_attention
+assert WordsLoss is agb.WordsLoss and SentenceLoss is agb.SentenceLoss
+# the rest of the reference's packages still resolve to the reference
+import networks.generator_submodules as gs
+import losses.gen_loss, losses.KL_loss, networks.rnn_encoder
+assert os.path.realpath(gs.__file__).startswith(os.path.realpath(ref))
+assert os.path.realpath(losses.gen_loss.__file__).startswith(os.path.realpath(ref))
+assert gs.AttentionModule is agb.AttentionModule, "GenNextStage would still build the reference attention"
+import networks, losses
+assert networks.attention.AttentionModule is agb.AttentionModule and losses.words_loss.WordsLoss is agb.WordsLoss
+print("install ok", order)
+'''
+
+
+def _fake_reference(tmp):
+    """a miniature tree with the reference's package layout and import lines (generator_submodules.py:10,
+    train.py:17,23-24)"""
+    files = {
+        "networks/__init__.py": "",
+        "networks/attention.py": "class AttentionModule: pass\ndef func_attention(*a): raise RuntimeError('reference')\n",
+        "networks/generator_submodules.py": "from .attention import AttentionModule\nclass GenNextStage: pass\n",
+        "networks/rnn_encoder.py": "class RNNEncoder: pass\n",
+        "losses/__init__.py": "",
+        "losses/words_loss.py": "from networks.attention import func_attention\nclass WordsLoss: pass\n",
+        "losses/sentence_loss.py": "class SentenceLoss: pass\n",
+        "losses/gen_loss.py": "class GenLoss: pass\n",
+        "losses/KL_loss.py": "class KLLoss: pass\n",
+    }
+    for rel, text in files.items():
+        path = os.path.join(tmp, rel)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as fh:
+            fh.write(text)
+    return tmp
+
+
+@pytest.mark.parametrize("order", ["before", "after"])
+@pytest.mark.parametrize("tree", ["fake", "real"])
+def test_install_routes_reference_imports_without_shadowing(tmp_path, order, tree):
+    """ADVICE r1: the drop-ins must not shadow the reference's `networks` / `losses` packages.  install() swaps
+    exactly the three hot-path modules; everything else of the reference stays importable."""
+    import subprocess
+    if tree == "real":
+        ref = "/root/reference"
+        if not os.path.isdir(os.path.join(ref, "networks")):
+            pytest.skip("the reference tree is only present in the build container")
+    else:
+        ref = _fake_reference(str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", _INSTALL_CHILD, ref, order, ROOT], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "install ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_no_cpu_fallback():
@@ -92,32 +157,36 @@ def test_product_never_imports_the_oracle():
 
 
 # ---- world_size-2 gloo test of the sharded exchange ------------------------------------------
-def _single_process_reference(seed):
+def _single_process_reference(seed, ragged=False):
     sys.path.insert(0, ROOT)
     from oracle import closed_form as cf
     from oracle import ref_port as rp
     img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(6, T=5, D=16, hw=3, seed=seed, n_classes=3)
+    if ragged:                      # the second rank's captions are all shorter than T: its RNN pads to T - 1 only
+        lens[3:] = torch.clamp(lens[3:], max=4)
     B, D = img.shape[:2]
     wl, _, dc, dw = cf.words_loss_fwd_bwd(img.numpy().reshape(B, D, -1), wrd.numpy(), labels.numpy(), lens.numpy(), cls)
     sl, _, dcnn, drnn = cf.sentence_loss_fwd_bwd(cnn.numpy(), rnn.numpy(), labels.numpy(), cls)
     return (img, wrd, cnn, rnn, labels, lens, cls), (wl, sl, dc.reshape(img.shape), dw, dcnn, drnn)
 
 
-def _worker(rank, world, port, seed, fused, out):
+def _worker(rank, world, port, seed, fused, out, ragged=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import attention_gan_b200  # noqa: F401  (puts the drop-ins on sys.path)
         import oracle_ops
-        from losses import damsm_core as core
-        (img, wrd, cnn, rnn, labels, lens, cls), _ = _single_process_reference(seed)
+        from attention_gan_b200.losses import damsm_core as core
+        (img, wrd, cnn, rnn, labels, lens, cls), _ = _single_process_reference(seed, ragged)
         n = img.shape[0] // world
         sl = slice(rank * n, rank * n + n)
         im = img[sl].clone().requires_grad_(True)
-        wd = wrd[sl].clone().requires_grad_(True)
+        wd = wrd[sl].clone()
+        if ragged and rank == 1:
+            wd = wd[:, :, :4].clone()                     # T differs per rank (rnn_encoder.py:89-92)
+        wd.requires_grad_(True)
         cn = cnn[sl].clone().requires_grad_(True)
         rn = rnn[sl].clone().requires_grad_(True)
         loc_labels = torch.arange(n)
@@ -129,6 +198,7 @@ def _worker(rank, world, port, seed, fused, out):
             wl, att = core.words_loss(im, wd, loc_labels, lens[sl], cls[sl], wcfg)
             sls = core.sentence_loss(cn, rn, loc_labels, cls[sl], scfg)
         (wl + sls).backward()
+        assert att.shape[1] == wd.shape[2]
         maps = core.split_att_maps(att, lens[sl], 3, 3)
         out[rank] = dict(wl=wl.item(), sl=sls.item(), dimg=im.grad.numpy(), dwords=wd.grad.numpy(),
                          dcnn=cn.grad.numpy(), drnn=rn.grad.numpy(), maps=[m.numpy() for m in maps])
@@ -158,3 +228,23 @@ def test_sharded_losses_equal_single_process(fused):
         np.testing.assert_allclose(o["drnn"], drnn0[sl], rtol=1e-4, atol=1e-6)
         for j, m in enumerate(o["maps"]):
             np.testing.assert_allclose(m, ref_maps[r * n + j].numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_sharded_losses_with_different_caption_padding_per_rank():
+    """the reference's RNN pads to the LOCAL batch's longest caption, so T can differ per rank; the
+    exchange pads to the agreed maximum and slices the word gradients back"""
+    world, seed = 2, 13
+    port = 29500 + (os.getpid() % 2000) + 19
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, seed, True, out, True), nprocs=world, join=True)
+    (img, wrd, cnn, rnn, labels, lens, cls), (wl0, sl0, dc0, dw0, dcnn0, drnn0) = _single_process_reference(seed, True)
+    n = img.shape[0] // world
+    for r in range(world):
+        o = out[r]
+        sl = slice(r * n, r * n + n)
+        assert abs(o["wl"] - wl0) < 1e-5 * abs(wl0) and abs(o["sl"] - sl0) < 1e-5 * abs(sl0)
+        np.testing.assert_allclose(o["dimg"], dc0[sl], rtol=1e-4, atol=1e-6)
+        T_r = 4 if r == 1 else 5
+        assert o["dwords"].shape[2] == T_r
+        np.testing.assert_allclose(o["dwords"], dw0[sl][:, :, :T_r], rtol=1e-4, atol=1e-6)

@@ -21,8 +21,8 @@ int word_attn_fwd_tc(const void* images, const float* we, const int64_t* mask, v
                      int B, int C, int HW, int T, int io_dtype, float qscale, cudaStream_t st);
 int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dctx_bs, const void* dattn, int C, int HW,
                                int T, int io_dtype);
-int word_attn_bwd_tc_ctas(int B, int HW);
-int word_attn_bwd_tc_grid(int B, int HW);
+int word_attn_bwd_tc_ctas(int B, int HW, int T);
+int word_attn_bwd_tc_grid(int B, int HW, int T);
 int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, const void* dctx, int64_t dctx_bs,
                      const void* dattn, void* dimages, float* part, int part_slots, float* dwe, int B, int C, int HW, int T, int io_dtype,
                      float scale, cudaStream_t st);
@@ -673,11 +673,11 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
   float* part = (float*)workspace;
   int rc = 0;
   const bool use_tc = tc::word_attn_bwd_tc_supported(images, dctx, dctx_bs, dattn, C, HW, T, io_dtype) != 0;
-  if (use_tc) ntiles = tc::word_attn_bwd_tc_ctas(B, HW);
+  if (use_tc) ntiles = tc::word_attn_bwd_tc_ctas(B, HW, T);
   float* dwe = part + (size_t)B * ntiles * C * T;
   int G = 0;                                      // 0: every partial slot is valid
   if (use_tc) {
-    G = tc::word_attn_bwd_tc_grid(B, HW);
+    G = tc::word_attn_bwd_tc_grid(B, HW, T);
     rc = tc::word_attn_bwd_tc(images, we, mask, dctx, dctx_bs, dattn, dimages, part, ntiles, nullptr, B, C, HW, T, io_dtype, scale, st);
     if (rc) return rc;
   } else {

@@ -558,8 +558,8 @@ struct AttnBwdParams {
   int d_rows;             // rows of the dctx tensor map per sample (= dctx batch stride / HW; C when contiguous)
 };
 
-constexpr int kBwdNT = 32;
-
+constexpr int kBwdNT = 32;      // word columns of the two-CTAs-per-SM variant (T <= 32)
+constexpr int kBwdNTLong = 64;  // long captions (32 < T <= 64, bf16 maps): one CTA per SM, 448 of the 512 TMEM columns
 
 // Persistent CTAs over contiguous, balanced ranges of the B * tiles pixel tiles (segments per sample,
 // see the forward kernel).  Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer, 2-5 / 6-9 =
@@ -572,11 +572,18 @@ constexpr int kBwdNT = 32;
 constexpr int kBwdThreads = 448;
 constexpr int kMaxBwdStages = 4;
 
-template <typename IO, int TL, int CT>
-__global__ void __launch_bounds__(kBwdThreads, 2)
+// TMEM columns per tile buffer u (UB = 2 NT + 32):  [0,NT) S -> ds hi | ds lo (bf16 pairs, NT/2 columns each),
+// [NT,2NT) G -> a (pairs, TL/2 columns) | ds in fp16 (fp16 maps, at NT + NT/2), [2NT, 2NT+32) dh;  the d(W.e)
+// accumulator [a part | ds part] (2 TL columns) follows the two buffers at 2 UB.
+template <typename IO, int NT, int TL, int CT>
+__global__ void __launch_bounds__(kBwdThreads, NT <= 32 ? 2 : 1)
 word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapD,
                         const AttnBwdParams p) {
-  constexpr int NT = kBwdNT;
+  static_assert(NT == 32 || NT == 64, "NT");
+  static_assert(TL <= NT && TL % 8 == 0, "TL");
+  static_assert(NT == 32 || !std::is_same<IO, __half>::value, "long captions: bf16 maps only");
+  constexpr uint32_t UB = 2 * NT + 32;
+  constexpr uint32_t kTmemCols = NT == 32 ? 256 : 512;
   constexpr int KB = TL / 8;
   constexpr int C = CT;
   const int nst = p.stages;
@@ -620,7 +627,7 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_base_s, 256);
+  if (warp == 0) tmem_alloc(tmem_base_s, kTmemCols);
   for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x) {
     const uint32_t one2 = pack2<IO>(1.f, 1.f);
     reinterpret_cast<uint4*>(sOnes)[i] = ((i >> 3) & 15) == 0 ? make_uint4(one2, one2, one2, one2) : make_uint4(0, 0, 0, 0);
@@ -631,7 +638,7 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_base_s;
   constexpr int fmt_io = std::is_same<IO, __nv_bfloat16>::value ? 1 : 0;
-  constexpr uint32_t kAccCol = 192;
+  constexpr uint32_t kAccCol = 2 * UB;
   const int q = warp & 3;
   const uint32_t lane0 = (uint32_t)(q * 32) << 16;
 
@@ -707,15 +714,15 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
               const int u = i1 & 1;
               tc_fence_after();
               const uint32_t st = smem_u32(sIn + (i1 % nst) * stage_bytes);
-              umma_f16(tmem + u * 96, d_ones, d_bias, idesc1, 0u);        // S = 0 / -inf per word
+              umma_f16(tmem + u * UB, d_ones, d_bias, idesc1, 0u);        // S = 0 / -inf per word
 #pragma unroll
               for (int kk = 0; kk < ks1; ++kk) {
                 const uint64_t dh_ = make_desc_sw128_mn_lbo(st + box + kk * 2048, (uint32_t)(2 * box));    // h
                 const uint64_t dd_ = make_desc_sw128_mn_lbo(st + kk * 2048, (uint32_t)(2 * box));          // dctx
-                umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s)) + 2 * kk, idesc1, 1u);
-                umma_f16(tmem + u * 96, dh_, make_desc_sw128(smem_u32(sB1s + NT * 128)) + 2 * kk, idesc1, 1u);
-                umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u)) + 2 * kk, idesc1, kk ? 1u : 0u);
-                umma_f16(tmem + u * 96 + NT, dd_, make_desc_sw128(smem_u32(sB1u + NT * 128)) + 2 * kk, idesc1, 1u);
+                umma_f16(tmem + u * UB, dh_, make_desc_sw128(smem_u32(sB1s)) + 2 * kk, idesc1, 1u);
+                umma_f16(tmem + u * UB, dh_, make_desc_sw128(smem_u32(sB1s + NT * 128)) + 2 * kk, idesc1, 1u);
+                umma_f16(tmem + u * UB + NT, dd_, make_desc_sw128(smem_u32(sB1u)) + 2 * kk, idesc1, kk ? 1u : 0u);
+                umma_f16(tmem + u * UB + NT, dd_, make_desc_sw128(smem_u32(sB1u + NT * 128)) + 2 * kk, idesc1, 1u);
               }
               umma_commit(&s_full[u]);
               ++j1;
@@ -726,12 +733,12 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
               tc_fence_after();
 #pragma unroll
               for (int kk = 0; kk < NT / 16; ++kk) {      // dh = ds (hi + lo) x W.e (hi + lo), lo*lo dropped
-                const uint32_t a_hi = tmem + u * 96 + kk * 8, a_lo = tmem + u * 96 + 16 + kk * 8;
+                const uint32_t a_hi = tmem + u * UB + kk * 8, a_lo = tmem + u * UB + NT / 2 + kk * 8;
                 const uint64_t b_hi = make_desc_sw128(smem_u32(sB2)) + 2 * kk;
                 const uint64_t b_lo = make_desc_sw128(smem_u32(sB2 + 32 * 128)) + 2 * kk;
-                umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_hi, idesc3, kk ? 1u : 0u);
-                umma_f16_ts(tmem + u * 96 + 2 * NT, a_lo, b_hi, idesc3, 1u);
-                umma_f16_ts(tmem + u * 96 + 2 * NT, a_hi, b_lo, idesc3, 1u);
+                umma_f16_ts(tmem + u * UB + 2 * NT, a_hi, b_hi, idesc3, kk ? 1u : 0u);
+                umma_f16_ts(tmem + u * UB + 2 * NT, a_lo, b_hi, idesc3, 1u);
+                umma_f16_ts(tmem + u * UB + 2 * NT, a_hi, b_lo, idesc3, 1u);
               }
               umma_commit(&dh_full[u]);
               const uint32_t st = smem_u32(sIn + s * stage_bytes);
@@ -759,61 +766,135 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
           const int it = it0 + j, k = it >> 1;
           mbar_wait(&s_full[u], k & 1);
           tc_fence_after();
-          float s[TL], g[TL];
-          tmem_ld_cols<TL>(tmem + lane0 + u * 96, s);
-          tmem_ld_cols<TL>(tmem + lane0 + u * 96 + NT, g);
-          tmem_ld_wait();
-          float mx = fmaxf(s[0], s[1]);
+          if constexpr (NT <= 32) {
+            float s[TL], g[TL];
+            tmem_ld_cols<TL>(tmem + lane0 + u * UB, s);
+            tmem_ld_cols<TL>(tmem + lane0 + u * UB + NT, g);
+            tmem_ld_wait();
+            float mx = fmaxf(s[0], s[1]);
 #pragma unroll
-          for (int t = 2; t < TL; t += 2) mx = fmaxf(mx, fmaxf(s[t], s[t + 1]));
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int t = 2; t < TL; t += 2) mx = fmaxf(mx, fmaxf(s[t], s[t + 1]));
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int t = 0; t < TL; ++t) {
-            s[t] = exp2f(s[t] - mx);
-            s4[t & 3] += s[t];
-          }
-          const float inv = __fdividef(1.f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
-          if (dattn != nullptr) {                      // rare: a gradient arrives through the attention maps too
+            for (int t = 0; t < TL; ++t) {
+              s[t] = exp2f(s[t] - mx);
+              s4[t & 3] += s[t];
+            }
+            const float inv = __fdividef(1.f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+            if (dattn != nullptr) {                      // rare: a gradient arrives through the attention maps too
+              const int pix = (sg.tile0 + j) * 128 + q * 32 + lane;
+#pragma unroll
+              for (int t = 0; t < TL; ++t)
+                if (t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)t * p.HW + pix]);
+            }
+            float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < TL; ++t) {
+              s[t] *= inv;
+              d4[t & 3] = fmaf(s[t], g[t], d4[t & 3]);
+            }
+            const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+            uint32_t hi[NT / 2], lo[NT / 2], pa[TL / 2];
+            uint32_t ph[kHalfIO ? TL / 2 : 1];
+#pragma unroll
+            for (int t = 0; t < NT; t += 2) {
+              if (t < TL) {
+                const float d0 = s[t] * (g[t] - dot), d1 = s[t + 1] * (g[t + 1] - dot);
+                const uint32_t h2 = pack2<__nv_bfloat16>(d0, d1);
+                hi[t / 2] = h2;
+                lo[t / 2] = pack2<__nv_bfloat16>(d0 - __uint_as_float(h2 << 16), d1 - __uint_as_float(h2 & 0xffff0000u));
+                pa[t / 2] = pack2<IO>(s[t], s[t + 1]);
+                if constexpr (kHalfIO) ph[t / 2] = pack2<IO>(d0, d1);
+              } else {
+                hi[t / 2] = 0u;
+                lo[t / 2] = 0u;
+              }
+            }
+            tmem_st_n<NT / 2>(tmem + lane0 + u * UB, hi);
+            tmem_st_n<NT / 2>(tmem + lane0 + u * UB + NT / 2, lo);
+            tmem_st_n<TL / 2>(tmem + lane0 + u * UB + NT, pa);
+            if constexpr (kHalfIO) tmem_st_n<TL / 2>(tmem + lane0 + u * UB + NT + NT / 2, ph);
+          } else {
+            // long captions: the probabilities stay in registers (TL values), the upstream gradients G are streamed
+            // from TMEM twice in chunks of 16 columns (dot product, then ds), so the live set stays near the
+            // 128 registers of a one-CTA-per-SM kernel (the same chunking under the 72-register cap of the
+            // two-CTAs-per-SM variant spills MORE than the straight version: measured with -Xptxas -v).  The packed results of chunk c land on columns that hold only consumed values:
+            // ds hi / lo over S (already in registers), a over the first half of G (chunk c covers G columns
+            // [16c, 16c+16), a of chunk c goes to [8c, 8c+8)).
+            float s[TL];
+            tmem_ld_cols<TL>(tmem + lane0 + u * UB, s);
+            tmem_ld_wait();
+            float mx = fmaxf(s[0], s[1]);
+#pragma unroll
+            for (int t = 2; t < TL; t += 2) mx = fmaxf(mx, fmaxf(s[t], s[t + 1]));
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < TL; ++t) {
+              s[t] = exp2f(s[t] - mx);
+              s4[t & 3] += s[t];
+            }
+            const float inv = __fdividef(1.f, (s4[0] + s4[1]) + (s4[2] + s4[3]));
             const int pix = (sg.tile0 + j) * 128 + q * 32 + lane;
+            float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int t = 0; t < TL; ++t)
-              if (t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)t * p.HW + pix]);
-          }
-          float d4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c0 = 0; c0 < TL; c0 += 16) {
+              constexpr int kW = 16;
+              float g[kW];
+              if (TL - c0 >= 16) tmem_ld16(tmem + lane0 + u * UB + NT + c0, g); else tmem_ld8(tmem + lane0 + u * UB + NT + c0, g);
+              tmem_ld_wait();
 #pragma unroll
-          for (int t = 0; t < TL; ++t) {
-            s[t] *= inv;
-            d4[t & 3] = fmaf(s[t], g[t], d4[t & 3]);
-          }
-          const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-          uint32_t hi[NT / 2], lo[NT / 2], pa[TL / 2];
-          uint32_t ph[kHalfIO ? TL / 2 : 1];
+              for (int t = 0; t < kW; ++t) {
+                if (c0 + t < TL) {
+                  if (dattn != nullptr && c0 + t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)(c0 + t) * p.HW + pix]);
+                  s[c0 + t] *= inv;
+                  d4[t & 3] = fmaf(s[c0 + t], g[t], d4[t & 3]);
+                }
+              }
+            }
+            const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
-          for (int t = 0; t < NT; t += 2) {
-            if (t < TL) {
-              const float d0 = s[t] * (g[t] - dot), d1 = s[t + 1] * (g[t + 1] - dot);
-              const uint32_t h2 = pack2<__nv_bfloat16>(d0, d1);
-              hi[t / 2] = h2;
-              lo[t / 2] = pack2<__nv_bfloat16>(d0 - __uint_as_float(h2 << 16), d1 - __uint_as_float(h2 & 0xffff0000u));
-              pa[t / 2] = pack2<IO>(s[t], s[t + 1]);
-              if constexpr (kHalfIO) ph[t / 2] = pack2<IO>(d0, d1);
-            } else {
-              hi[t / 2] = 0u;
-              lo[t / 2] = 0u;
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+              uint32_t hi[8], lo[8], pa[8];
+              if (c0 < TL) {
+                float g[16];
+                if (TL - c0 >= 16) tmem_ld16(tmem + lane0 + u * UB + NT + c0, g); else tmem_ld8(tmem + lane0 + u * UB + NT + c0, g);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 16; t += 2) {
+                  if (c0 + t < TL) {
+                    float g0 = g[t], g1 = g[t + 1];
+                    if (dattn != nullptr && pix < p.HW) {
+                      if (c0 + t < p.T) g0 += to_f32(dattn[(size_t)(c0 + t) * p.HW + pix]);
+                      if (c0 + t + 1 < p.T) g1 += to_f32(dattn[(size_t)(c0 + t + 1) * p.HW + pix]);
+                    }
+                    const float d0 = s[c0 + t] * (g0 - dot), d1 = s[c0 + t + 1] * (g1 - dot);
+                    const uint32_t h2 = pack2<__nv_bfloat16>(d0, d1);
+                    hi[t / 2] = h2;
+                    lo[t / 2] = pack2<__nv_bfloat16>(d0 - __uint_as_float(h2 << 16), d1 - __uint_as_float(h2 & 0xffff0000u));
+                    pa[t / 2] = pack2<IO>(s[c0 + t], s[c0 + t + 1]);
+                  } else {
+                    hi[t / 2] = 0u;
+                    lo[t / 2] = 0u;
+                    pa[t / 2] = 0u;
+                  }
+                }
+                if (TL - c0 >= 16) tmem_st8(tmem + lane0 + u * UB + NT + c0 / 2, pa); else tmem_st4(tmem + lane0 + u * UB + NT + c0 / 2, pa);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) hi[k] = lo[k] = 0u;
+              }
+              tmem_st8(tmem + lane0 + u * UB + c0 / 2, hi);
+              tmem_st8(tmem + lane0 + u * UB + NT / 2 + c0 / 2, lo);
             }
           }
-          tmem_st_n<NT / 2>(tmem + lane0 + u * 96, hi);
-          tmem_st_n<NT / 2>(tmem + lane0 + u * 96 + 16, lo);
-          tmem_st_n<TL / 2>(tmem + lane0 + u * 96 + 32, pa);
-          if constexpr (kHalfIO) tmem_st_n<TL / 2>(tmem + lane0 + u * 96 + 48, ph);
           tmem_st_wait();
           // read a and ds back as stmatrix fragments: [a | ds] transposed into the B operand of GEMM4
           uint32_t fa[2][2 * KB], fd[2][2 * KB];
-          constexpr int kDsCol = kHalfIO ? 48 : 0;
-          tmem_ld_packed<KB>(tmem + lane0 + u * 96 + 32, fa[0]);
-          tmem_ld_packed<KB>(tmem + lane0 + kHalfLanes + u * 96 + 32, fa[1]);
-          tmem_ld_packed<KB>(tmem + lane0 + u * 96 + kDsCol, fd[0]);
-          tmem_ld_packed<KB>(tmem + lane0 + kHalfLanes + u * 96 + kDsCol, fd[1]);
+          constexpr int kDsCol = kHalfIO ? NT + NT / 2 : 0;
+          tmem_ld_packed<KB>(tmem + lane0 + u * UB + NT, fa[0]);
+          tmem_ld_packed<KB>(tmem + lane0 + kHalfLanes + u * UB + NT, fa[1]);
+          tmem_ld_packed<KB>(tmem + lane0 + u * UB + kDsCol, fd[0]);
+          tmem_ld_packed<KB>(tmem + lane0 + kHalfLanes + u * UB + kDsCol, fd[1]);
           tmem_ld_wait();
 #pragma unroll
           for (int kk = 0; kk < KB; ++kk) {
@@ -837,8 +918,8 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
           mbar_wait(&dh_full[u], k & 1);
           tc_fence_after();
           float w[2][4 * (C / 8)];
-          tmem_ld_frag<C / 8>(tmem + lane0 + u * 96 + 2 * NT, w[0]);
-          tmem_ld_frag<C / 8>(tmem + lane0 + kHalfLanes + u * 96 + 2 * NT, w[1]);
+          tmem_ld_frag<C / 8>(tmem + lane0 + u * UB + 2 * NT, w[0]);
+          tmem_ld_frag<C / 8>(tmem + lane0 + kHalfLanes + u * UB + 2 * NT, w[1]);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
@@ -868,21 +949,27 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
           float* sX = reinterpret_cast<float*>(sStD);          // [C][TL] exchange between the two row groups
           mbar_wait(acc_done, seg & 1);
           tc_fence_after();
-          float va[TL], vd[TL];
-          tmem_ld_cols<TL>(tmem + lane0 + kAccCol, va);         // rows of dctx x columns of a
-          tmem_ld_cols<TL>(tmem + lane0 + kAccCol + TL, vd);    // rows of h x columns of ds
-          tmem_ld_wait();
-          tc_fence_before();
           named_bar_sync(2, 128);                               // staging reads of the last tile are done
-          if (px >= C && px < 2 * C) {
+          {
+            float vd[TL];
+            tmem_ld_cols<TL>(tmem + lane0 + kAccCol + TL, vd);  // rows of h x columns of ds
+            tmem_ld_wait();
+            if (px >= C && px < 2 * C) {
 #pragma unroll
-            for (int t = 0; t < TL; ++t) sX[(px - C) * TL + t] = vd[t];
+              for (int t = 0; t < TL; ++t) sX[(px - C) * TL + t] = vd[t];
+            }
           }
           named_bar_sync(2, 128);
-          if (px < C) {
+          {
+            float va[TL];
+            tmem_ld_cols<TL>(tmem + lane0 + kAccCol, va);       // rows of dctx x columns of a
+            tmem_ld_wait();
+            tc_fence_before();
+            if (px < C) {
 #pragma unroll
-            for (int t = 0; t < TL; ++t)
-              if (t < p.T) part[px * p.T + t] = va[t] + p.scale * sX[px * TL + t];
+              for (int t = 0; t < TL; ++t)
+                if (t < p.T) part[px * p.T + t] = va[t] + p.scale * sX[px * TL + t];
+            }
           }
           named_bar_sync(2, 128);
           (void)dtid;
@@ -896,33 +983,34 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
 int word_attn_bwd_tc_supported(const void* images, const void* dctx, int64_t dctx_bs, const void* dattn, int C, int HW,
                                int T, int io_dtype) {
   if (io_dtype != AGB_BF16 && io_dtype != AGB_F16) return 0;
-  if ((C != 16 && C != 32) || T > kBwdNT || HW % 8 != 0) return 0;
+  if ((C != 16 && C != 32) || T > kBwdNTLong || HW % 8 != 0) return 0;
+  if (T > kBwdNT && io_dtype != AGB_BF16) return 0;   // long captions: bf16 maps (fp16 would need a fourth packed operand in TMEM)
   // dctx may be a channel slice of a wider [B, C', HW] gradient (GenNextStage's concat buffer): whole rows only
   if (dctx_bs < (int64_t)C * HW || dctx_bs % HW != 0) return 0;
   if ((((uintptr_t)images | (uintptr_t)dctx) & 15) != 0) return 0;
   return 1;
 }
 
-// persistent grid of the backward kernel: 2 CTAs per SM, never more CTAs than tiles
-int word_attn_bwd_tc_grid(int B, int HW) {
+// persistent grid of the backward kernel: 2 CTAs per SM (1 for long captions), never more CTAs than tiles
+int word_attn_bwd_tc_grid(int B, int HW, int T) {
   const int sms = device_sms();
   if (options().attn_bwd_ctas > 0)   // tuning knob
     return (int)std::min<long long>(options().attn_bwd_ctas, (long long)B * cdiv(HW, 128));
-  return persistent_grid((long long)sms * 2, B, cdiv(HW, 128));
+  return persistent_grid((long long)sms * (T > kBwdNT ? 1 : 2), B, cdiv(HW, 128));
 }
 
 // number of per-sample partial-sum slots the backward kernel may write: the CTAs whose tile range
 // overlaps one sample (ranges are floor(total/G) or one more tiles long)
-int word_attn_bwd_tc_ctas(int B, int HW) {
+int word_attn_bwd_tc_ctas(int B, int HW, int T) {
   const int tiles = cdiv(HW, 128);
   const long long total = (long long)B * tiles;
-  const long long m = std::max<long long>(1, total / word_attn_bwd_tc_grid(B, HW));
+  const long long m = std::max<long long>(1, total / word_attn_bwd_tc_grid(B, HW, T));
   return (int)std::min<long long>(tiles, (tiles - 1) / m + 2);
 }
 
@@ -954,39 +1042,47 @@ int word_attn_bwd_tc(const void* images, const float* we, const int64_t* mask, c
   p.ctas_per_sample = 0;
   p.d_rows = d_rows;
   p.part_slots = part_slots;
-  const int NT = kBwdNT;
+  const int NT = T > kBwdNT ? kBwdNTLong : kBwdNT;
+  const int per_sm = T > kBwdNT ? 1 : 2;
   const int TL = (T + 7) / 8 * 8;
   const int fixed = 4 * NT * 128 + 2 * 32 * 128 + 2 * 2 * (2 * TL) * 128 + 4096 + NT * 128 + 2 * C * 128 + 256;
-  // deepest input ring that still lets two CTAs share the SM's 227 KB (1 KB reserved per CTA)
-  int stages = ((227 * 1024) / 2 - 1024 - fixed) / (4 * C * 128);
+  // deepest input ring that still lets per_sm CTAs share the SM's 227 KB (1 KB reserved per CTA)
+  int stages = ((227 * 1024) / per_sm - 1024 - fixed) / (4 * C * 128);
   stages = std::max(2, std::min(kMaxBwdStages, stages));
   if (options().attn_bwd_stages > 0) stages = std::max(2, std::min(kMaxBwdStages, options().attn_bwd_stages));   // tuning knob
   p.stages = stages;
   const int smem = stages * 4 * C * 128 + fixed;
-  const int grid = word_attn_bwd_tc_grid(B, HW);
+  const int grid = word_attn_bwd_tc_grid(B, HW, T);
   const int slot = prof_begin(PROF_ATTN_BWD, st);
-#define AGB_ATTN_BWD_CASE2(TLV, CTV)                                                              \
-  if (bf) {                                                                                       \
-    auto kern = word_attn_bwd_tc_kernel<__nv_bfloat16, TLV, CTV>;                                 \
-    AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-    kern<<<grid, kBwdThreads, smem, st>>>(mapH, mapD, p);                                         \
-  } else {                                                                                        \
-    auto kern = word_attn_bwd_tc_kernel<__half, TLV, CTV>;                                        \
+#define AGB_ATTN_BWD_LAUNCH(IOT, NTV, TLV, CTV)                                                    \
+  {                                                                                               \
+    auto kern = word_attn_bwd_tc_kernel<IOT, NTV, TLV, CTV>;                                      \
     AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
     kern<<<grid, kBwdThreads, smem, st>>>(mapH, mapD, p);                                         \
   }
+#define AGB_ATTN_BWD_CASE2(TLV, CTV)                                                              \
+  if (bf) AGB_ATTN_BWD_LAUNCH(__nv_bfloat16, 32, TLV, CTV) else AGB_ATTN_BWD_LAUNCH(__half, 32, TLV, CTV)
 #define AGB_ATTN_BWD_CASE(TLV)        \
   if (C == 16) {                      \
     AGB_ATTN_BWD_CASE2(TLV, 16)       \
   } else {                            \
     AGB_ATTN_BWD_CASE2(TLV, 32)       \
   }
+#define AGB_ATTN_BWD_LONG(TLV)                                      \
+  if (C == 16) AGB_ATTN_BWD_LAUNCH(__nv_bfloat16, 64, TLV, 16)      \
+  else AGB_ATTN_BWD_LAUNCH(__nv_bfloat16, 64, TLV, 32)
   switch ((T + 7) / 8) {
     case 1: AGB_ATTN_BWD_CASE(8) break;
     case 2: AGB_ATTN_BWD_CASE(16) break;
     case 3: AGB_ATTN_BWD_CASE(24) break;
-    default: AGB_ATTN_BWD_CASE(32) break;
+    case 4: AGB_ATTN_BWD_CASE(32) break;
+    case 5: AGB_ATTN_BWD_LONG(40) break;
+    case 6: AGB_ATTN_BWD_LONG(48) break;
+    case 7: AGB_ATTN_BWD_LONG(56) break;
+    default: AGB_ATTN_BWD_LONG(64) break;
   }
+#undef AGB_ATTN_BWD_LAUNCH
+#undef AGB_ATTN_BWD_LONG
 #undef AGB_ATTN_BWD_CASE2
 #undef AGB_ATTN_BWD_CASE
   prof_end(slot, st);

@@ -36,7 +36,10 @@ CASES = [
     (600, 16, 18, 32, False),   # 2 tiles per sample: one CTA walks through several samples
     (5, 48, 32, 16, True),      # T = 32 (limit of the tensor-core backward), C = 16, gradient through the maps
     (3, 40, 7, 32, True),       # HW = 1600 is not a multiple of the 128-pixel tile; fewer than 8 words
-    (2, 24, 64, 32, False),     # T = 64: forward on tensor cores, backward on the CUDA-core kernel
+    (2, 24, 64, 32, False),     # T = 64: long-caption kernels (bf16: tensor-core backward, one CTA per SM; fp16: CUDA cores)
+    (3, 32, 40, 32, True),      # T = 40: long-caption backward with a ragged last chunk of 8 words + gradient through the maps
+    (20, 16, 50, 16, False),    # T = 50, C = 16, two tiles per sample: segments of several samples per CTA
+    (2, 64, 64, 32, True),      # T = 64 with d attn: 32 tiles per sample, many tiles per CTA
     (7, 32, 18, 64, False),     # C = 64: forward on tensor cores (1 CTA per SM), backward on CUDA cores
 ]
 

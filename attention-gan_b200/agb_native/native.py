@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libattngan_b200.so")
 
 AGB_F32, AGB_BF16, AGB_F16 = 0, 1, 2
-AGB_MATH_FP32, AGB_MATH_TC_F16, AGB_MATH_TC_BF16 = 0, 1, 2
+AGB_MATH_FP32, AGB_MATH_TC_F16, AGB_MATH_TC_BF16, AGB_MATH_TC_F16X2 = 0, 1, 2, 3
 AGB_MATH_SAVE = 0x100   # flag for agb_damsm_fwd: training forward (see include/attngan_b200.h)
-MATH_NAMES = {"fp32": AGB_MATH_FP32, "f16": AGB_MATH_TC_F16, "bf16": AGB_MATH_TC_BF16}
+MATH_NAMES = {"fp32": AGB_MATH_FP32, "f16": AGB_MATH_TC_F16, "bf16": AGB_MATH_TC_BF16, "f16x2": AGB_MATH_TC_F16X2}
 
 # name -> (restype, argtypes); mirrors include/attngan_b200.h one to one
 SIGNATURES = {

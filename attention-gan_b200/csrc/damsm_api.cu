@@ -15,7 +15,7 @@ int damsm_fp32_bwd(const float* img, const float* words, int64_t ws_b, int64_t w
 int sent_cos_fwd_launch(const float* cnn, const float* rnn, int Bi, int Bc, int D, float eps,
                         float* scos_out, cudaStream_t st);
 #ifdef AGB_WITH_TC
-size_t damsm_tc_workspace_bytes(int Bi, int Bc, int T, int D, int R);
+size_t damsm_tc_workspace_bytes(int Bi, int Bc, int T, int D, int R, int math);
 int damsm_tc_supported(int T, int D, int R);
 int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1,
@@ -43,7 +43,7 @@ extern "C" int agb_damsm_supported(int T, int D, int R, int math) {
   if (T <= 0 || D <= 0 || R <= 0) return 0;
   if (math == AGB_MATH_FP32) return (T <= 64 && R <= 1024) ? 1 : 0;
 #ifdef AGB_WITH_TC
-  if (math == AGB_MATH_TC_F16 || math == AGB_MATH_TC_BF16) return damsm_tc_supported(T, D, R);
+  if (math == AGB_MATH_TC_F16 || math == AGB_MATH_TC_BF16 || math == AGB_MATH_TC_F16X2) return damsm_tc_supported(T, D, R);
 #endif
   return 0;
 }
@@ -53,7 +53,7 @@ extern "C" size_t agb_damsm_workspace_bytes(int Bi, int Bc, int T, int D, int R,
   if (Bi <= 0 || Bc <= 0 || !agb_damsm_supported(T, D, R, math)) return 0;
   if (math == AGB_MATH_FP32) return damsm_fp32_workspace_bytes(Bi, Bc, T, D, R);
 #ifdef AGB_WITH_TC
-  return damsm_tc_workspace_bytes(Bi, Bc, T, D, R);
+  return damsm_tc_workspace_bytes(Bi, Bc, T, D, R, math);
 #else
   return 0;
 #endif

@@ -67,14 +67,38 @@ template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u)
 // ---------------------------------------------------------------------------------------------
 // pack kernels
 // ---------------------------------------------------------------------------------------------
-// greedy packing of whole captions into tiles of <= 128 word rows (and <= 128 captions)
-// tile_cpre[t] = exclusive prefix of the per-item cost estimate of word tile t (see cta_items_balanced)
-__global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, int T, int32_t* __restrict__ cap_row,
+// greedy packing of whole captions into units of <= U word rows (U = 128: one unit per tile; U = 64 in split
+// precision: two units per tile, so that no caption straddles a 64-row boundary) and <= U captions.
+// tile_cpre[t] = exclusive prefix of the per-item cost estimate of word tile t (see cta_items_balanced).
+// unit_first / unit_ncap / nunits (U = 64 only): the caption range of every half tile; nunits = 2 * ntiles
+// (a trailing half tile without captions is emitted when the count is odd).
+__global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, int T, int U, int32_t* __restrict__ cap_row,
                                  int32_t* __restrict__ tile_first, int32_t* __restrict__ tile_ncap,
-                                 int32_t* __restrict__ ntiles, int32_t* __restrict__ tile_cpre) {
+                                 int32_t* __restrict__ ntiles, int32_t* __restrict__ tile_cpre,
+                                 int32_t* __restrict__ unit_first, int32_t* __restrict__ unit_ncap,
+                                 int32_t* __restrict__ nunits) {
   __shared__ int lens_s[1024];
-  int row = 0, tile = 0, first = 0;
+  const int upt = kTileN / U;                 // units per tile
+  int row = 0, unit = 0, first = 0, tfirst = 0;
   int cost = kItemCost0, cpre = 0;
+  auto close_unit = [&](int next_first) {
+    if (unit_first) {
+      unit_first[unit] = first;
+      unit_ncap[unit] = next_first - first;
+    }
+    if ((unit + 1) % upt == 0) {              // the tile is complete
+      const int tile = unit / upt;
+      tile_first[tile] = tfirst;
+      tile_ncap[tile] = next_first - tfirst;
+      tile_cpre[tile] = cpre;
+      cpre += cost;
+      cost = kItemCost0;
+      tfirst = next_first;
+    }
+    ++unit;
+    first = next_first;
+    row = 0;
+  };
   for (int base = 0; base < Bc; base += 1024) {
     const int n = min(1024, Bc - base);
     __syncthreads();
@@ -84,36 +108,28 @@ __global__ void tile_pack_kernel(const int32_t* __restrict__ cap_lens, int Bc, i
       for (int k = 0; k < n; ++k) {
         const int i = base + k, L = lens_s[k];
         // the epilogues read a caption's TMEM columns in windows of 4: keep the whole window inside the
-        // tile (the last accumulator buffer ends at TMEM column 512)
-        if (row + ((L + 3) & ~3) > kTileN || i - first == 128) {
-          tile_first[tile] = first;
-          tile_ncap[tile] = i - first;
-          tile_cpre[tile] = cpre;
-          cpre += cost;
-          cost = kItemCost0;
-          ++tile;
-          first = i;
-          row = 0;
-        }
-        cap_row[i] = tile * kTileN + row;
+        // unit (the last accumulator buffer ends at TMEM column 512)
+        if (row + ((L + 3) & ~3) > U || i - first == U) close_unit(i);
+        cap_row[i] = unit * U + row;
         row += L;
         if (L > 0) cost += ((L + 3) & ~3) + kItemCostCap;
       }
     }
   }
   if (threadIdx.x == 0) {
-    tile_first[tile] = first;
-    tile_ncap[tile] = Bc - first;
-    tile_cpre[tile] = cpre;
-    tile_cpre[tile + 1] = cpre + cost;
-    ntiles[0] = tile + 1;
+    close_unit(Bc);
+    while (unit % upt != 0) close_unit(Bc);   // pad the last tile with empty units
+    const int nt = unit / upt;
+    tile_cpre[nt] = cpre;
+    ntiles[0] = nt;
+    if (nunits) nunits[0] = unit;
   }
 }
 
 template <typename T16>
 __global__ void pack_words_kernel_tc(const float* __restrict__ words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                                      const int32_t* __restrict__ cap_lens, const int32_t* __restrict__ cap_row,
-                                     T16* __restrict__ Wh, float* __restrict__ pn, int T) {
+                                     T16* __restrict__ Wh, T16* __restrict__ Wl, float* __restrict__ pn, int T) {
   const int i = blockIdx.x, t = blockIdx.y;
   const int L = min(max(cap_lens[i], 0), T);
   if (t >= L) return;
@@ -122,7 +138,9 @@ __global__ void pack_words_kernel_tc(const float* __restrict__ words, int64_t ws
   float ss = 0.f;
   for (int d = threadIdx.x; d < kD; d += blockDim.x) {
     const float v = src[(int64_t)d * ws_d];
-    Wh[row * kD + d] = cvt16<T16>(v);
+    const T16 h = cvt16<T16>(v);
+    Wh[row * kD + d] = h;
+    if (Wl) Wl[row * kD + d] = cvt16<T16>(v - to_f32(h));       // split precision: w = hi + lo
     ss = fmaf(v, v, ss);
   }
   __shared__ float red[8];
@@ -138,7 +156,8 @@ __global__ void pack_words_kernel_tc(const float* __restrict__ words, int64_t ws
 
 // img [Bi,256,R] fp32 -> Ck [Bi*256, 320] (same orientation, padded) and Ct [Bi*384, 256] (transposed)
 template <typename T16>
-__global__ void pack_img_kernel_tc(const float* __restrict__ img, T16* __restrict__ Ck, T16* __restrict__ Ct, int R) {
+__global__ void pack_img_kernel_tc(const float* __restrict__ img, T16* __restrict__ Ck, T16* __restrict__ Ct,
+                                   T16* __restrict__ Ckl, T16* __restrict__ Ctl, int R) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, d0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // r0 < 384
   const int tx = threadIdx.x, ty = threadIdx.y;                            // 32 x 8
@@ -146,12 +165,19 @@ __global__ void pack_img_kernel_tc(const float* __restrict__ img, T16* __restric
     const int d = d0 + k, r = r0 + tx;
     const float v = (r < R) ? img[((size_t)b * kD + d) * R + r] : 0.f;
     tile[k][tx] = v;
-    if (r < kRCols) Ck[((size_t)b * kD + d) * kRCols + r] = cvt16<T16>(v);
+    if (r < kRCols) {
+      const T16 h = cvt16<T16>(v);
+      Ck[((size_t)b * kD + d) * kRCols + r] = h;
+      if (Ckl) Ckl[((size_t)b * kD + d) * kRCols + r] = cvt16<T16>(v - to_f32(h));
+    }
   }
   __syncthreads();
   for (int k = ty; k < 32; k += 8) {
     const int r = r0 + k, d = d0 + tx;
-    Ct[((size_t)b * kRRows + r) * kD + d] = cvt16<T16>(tile[tx][k]);
+    const float v = tile[tx][k];
+    const T16 h = cvt16<T16>(v);
+    Ct[((size_t)b * kRRows + r) * kD + d] = h;
+    if (Ctl) Ctl[((size_t)b * kRRows + r) * kD + d] = cvt16<T16>(v - to_f32(h));
   }
 }
 
@@ -248,6 +274,7 @@ struct FwdParams {
 };
 
 #include "damsm_tc_fwd2.inc"
+#include "damsm_tc_fwd2x.inc"
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -263,13 +290,23 @@ struct TcPlan {
   // context vectors would not fit the budget (or AGB_DAMSM_BWD=2) and the backward recomputes (damsm_bwd2_kernel)
   int save;
   size_t off_v16, off_rowst;
+  // split precision (AGB_MATH_TC_F16X2): captions packed into 64-row half tiles, lo parts of every operand
+  int split;
+  size_t off_Wl, off_Ctl, off_Ckl, off_ufirst, off_uncap, off_nunits;
 };
 
-static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
+static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R, bool split) {
   const Options& opt = options();
   TcPlan p;
-  const int per_tile = 128 / ((T + 3) & ~3);  // captions that always fit in one tile (4-column windows)
-  p.nt_max = (Bc + per_tile - 1) / per_tile;
+  p.split = split ? 1 : 0;
+  const int window = (T + 3) & ~3;              // a caption's TMEM columns are read in windows of 4
+  if (split) {
+    const int per_unit = 64 / window;           // captions that always fit in one 64-row half tile
+    p.nt_max = ((Bc + per_unit - 1) / per_unit + 1) / 2;
+  } else {
+    const int per_tile = 128 / window;          // captions that always fit in one tile
+    p.nt_max = (Bc + per_tile - 1) / per_tile;
+  }
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 1024); return at; };
   p.off_Wh = take((size_t)p.nt_max * kTileN * kD * 2);
@@ -283,6 +320,15 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R) {
   p.off_Ck = take((size_t)Bi * kD * kRCols * 2);
   p.off_attS = take((size_t)Bi * T * R * 4);
   p.off_attB = take((size_t)Bi * T * R * 4);
+  p.off_Wl = p.off_Ctl = p.off_Ckl = p.off_ufirst = p.off_uncap = p.off_nunits = 0;
+  if (split) {
+    p.off_Wl = take((size_t)p.nt_max * kTileN * kD * 2);
+    p.off_Ctl = take((size_t)Bi * kRRows * kD * 2);
+    p.off_Ckl = take((size_t)Bi * kD * kRCols * 2);
+    p.off_ufirst = take((size_t)2 * p.nt_max * 4);
+    p.off_uncap = take((size_t)2 * p.nt_max * 4);
+    p.off_nunits = take(256);
+  }
   const size_t all_rows = (size_t)Bi * p.nt_max * kTileN;
   p.save = (all_rows * (kD * 2 + 16) <= (size_t)std::max<long long>(0, opt.damsm_save_bytes) && opt.damsm_bwd != 2) ? 1 : 0;
   // staging of one backward chunk: E16 + A116 (+ dV16 for the recomputing backward) + dpp per (image, word row)
@@ -312,6 +358,7 @@ static int num_sms() { return device_sms(); }
 
 struct Packed {
   void* Wh; float* pn; int32_t *cap_row, *tfirst, *tncap, *tcpre, *ntiles; void* Ct; void* Ck;
+  void *Wl, *Ctl, *Ckl; int32_t *ufirst, *uncap, *nunits;     // split precision only
 };
 
 // pack the operands of one call: caption tiles, 16-bit words, 16-bit region features (both layouts)
@@ -328,16 +375,25 @@ static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t 
   int32_t* ntiles = (int32_t*)(ws + pl.off_ntiles);
   T16* Ct = (T16*)(ws + pl.off_Ct);
   T16* Ck = (T16*)(ws + pl.off_Ck);
+  T16* Wl = pl.split ? (T16*)(ws + pl.off_Wl) : nullptr;
+  T16* Ctl = pl.split ? (T16*)(ws + pl.off_Ctl) : nullptr;
+  T16* Ckl = pl.split ? (T16*)(ws + pl.off_Ckl) : nullptr;
+  int32_t* ufirst = pl.split ? (int32_t*)(ws + pl.off_ufirst) : nullptr;
+  int32_t* uncap = pl.split ? (int32_t*)(ws + pl.off_uncap) : nullptr;
+  int32_t* nunits = pl.split ? (int32_t*)(ws + pl.off_nunits) : nullptr;
   if (!already_packed) {
     AGB_CUDA(cudaMemsetAsync(Wh, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
+    if (Wl) AGB_CUDA(cudaMemsetAsync(Wl, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
     AGB_CUDA(cudaMemsetAsync(pn, 0, (size_t)pl.nt_max * kTileN * 4, st));
-    tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, cap_row, tfirst, tncap, ntiles, tcpre);
+    tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, pl.split ? 64 : kTileN, cap_row, tfirst, tncap, ntiles, tcpre,
+                                        ufirst, uncap, nunits);
     if (int rc = check_launch("tile_pack_kernel")) return rc;
-    pack_words_kernel_tc<T16><<<dim3(Bc, T), 128, 0, st>>>(words, ws_b, ws_d, ws_t, cap_lens, cap_row, Wh, pn, T);
+    pack_words_kernel_tc<T16><<<dim3(Bc, T), 128, 0, st>>>(words, ws_b, ws_d, ws_t, cap_lens, cap_row, Wh, Wl, pn, T);
     if (int rc = check_launch("pack_words_kernel_tc")) return rc;
-    pack_img_kernel_tc<T16><<<dim3(kRRows / 32, kD / 32, Bi), dim3(32, 8), 0, st>>>(img, Ck, Ct, R);
+    pack_img_kernel_tc<T16><<<dim3(kRRows / 32, kD / 32, Bi), dim3(32, 8), 0, st>>>(img, Ck, Ct, Ckl, Ctl, R);
     if (int rc = check_launch("pack_img_kernel_tc")) return rc;
   }
+  out->Wl = Wl; out->Ctl = Ctl; out->Ckl = Ckl; out->ufirst = ufirst; out->uncap = uncap; out->nunits = nunits;
   out->Wh = Wh; out->pn = pn; out->cap_row = cap_row; out->tfirst = tfirst; out->tncap = tncap; out->tcpre = tcpre; out->ntiles = ntiles;
   out->Ct = Ct; out->Ck = Ck;
   return 0;
@@ -374,6 +430,27 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
   p.g1_log2 = gamma1 * kLog2e;
   p.gamma2 = gamma2;
   p.v16 = ws + pl.off_v16; p.rowst = (float4*)(ws + pl.off_rowst); p.Ntot = pl.nt_max * kTileN;
+  if (pl.split) {
+    if constexpr (std::is_same<T16, __half>::value) {
+      CUtensorMap mapWh, mapWl, mapCtl, mapCkl;
+      if (int rc = make_tmap_2d(&mapWh, pk.Wh, (uint64_t)pl.nt_max * kTileN, kD, 64, false)) return rc;
+      if (int rc = make_tmap_2d(&mapWl, pk.Wl, (uint64_t)pl.nt_max * kTileN, kD, 64, false)) return rc;
+      if (int rc = make_tmap_2d(&mapCtl, pk.Ctl, (uint64_t)Bi * kRRows, kD, 128, false)) return rc;
+      if (int rc = make_tmap_2d(&mapCkl, pk.Ckl, (uint64_t)Bi * kD, kRCols, 128, false)) return rc;
+      FwdXParams xp;
+      xp.f = p; xp.unit_first = pk.ufirst; xp.unit_ncap = pk.uncap; xp.nunits = pk.nunits;
+      auto kx = save ? damsm_fwd2x_kernel<true> : damsm_fwd2x_kernel<false>;
+      AGB_CUDA(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+      const long long max_items_x = (long long)Bi * pl.nt_max * 2;
+      const int grid_x = (int)std::min<long long>(num_sms(), max_items_x);
+      const int slot_x = prof_begin(PROF_DAMSM_TC_FWD, st);
+      kx<<<grid_x, kThreads, kSmemBytes2, st>>>(mapWh, mapWl, mapCt, mapCtl, mapCk, mapCkl, xp);
+      prof_end(slot_x, st);
+      return check_launch("damsm_fwd2x_kernel");
+    } else {
+      return fail_unsupported("split precision needs fp16 operands");
+    }
+  }
   auto kern = save ? damsm_fwd2_kernel<T16, true> : damsm_fwd2_kernel<T16, false>;
   AGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
   const long long max_items = (long long)Bi * pl.nt_max;
@@ -392,7 +469,9 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
 
 int damsm_tc_supported(int T, int D, int R) { return (D == tc::kD && T >= 1 && T <= 32 && R >= 1 && R <= tc::kRCols) ? 1 : 0; }
 
-size_t damsm_tc_workspace_bytes(int Bi, int Bc, int T, int D, int R) { return tc::make_tc_plan(Bi, Bc, T, D, R).total; }
+size_t damsm_tc_workspace_bytes(int Bi, int Bc, int T, int D, int R, int math) {
+  return tc::make_tc_plan(Bi, Bc, T, D, R, math == AGB_MATH_TC_F16X2).total;
+}
 
 int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_d, int64_t ws_t,
                  const int32_t* cap_lens, int Bi, int Bc, int T, int D, int R, float gamma1, float gamma2,
@@ -400,8 +479,8 @@ int damsm_tc_fwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
                  float* scos_out, void* workspace, size_t workspace_bytes, int math, int save, cudaStream_t st) {
   if (Bi <= 0 || Bc <= 0) return fail_arg("non-positive batch");
   if (Bi > 65535) return fail_unsupported("Bi=%d > 65535", Bi);
-  if (math == AGB_MATH_TC_F16 && gamma1 > 11.f) return fail_unsupported("gamma1=%g overflows fp16 (use bf16 or fp32 math)", gamma1);
-  const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R);
+  if (math != AGB_MATH_TC_BF16 && gamma1 > 11.f) return fail_unsupported("gamma1=%g overflows fp16 (use bf16 or fp32 math)", gamma1);
+  const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R, math == AGB_MATH_TC_F16X2);
   if (workspace_bytes < pl.total) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
     return AGB_E_WORKSPACE;
@@ -441,7 +520,7 @@ int damsm_tc_bwd(const float* img, const float* words, int64_t ws_b, int64_t ws_
                  void* workspace, size_t workspace_bytes, int ws_from_fwd, int math, cudaStream_t st) {
   if (Bi <= 0 || Bc <= 0) return fail_arg("non-positive batch");
   if (Bi > 65535) return fail_unsupported("Bi=%d > 65535", Bi);
-  const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R);
+  const tc::TcPlan pl = tc::make_tc_plan(Bi, Bc, T, D, R, math == AGB_MATH_TC_F16X2);
   if (workspace_bytes < pl.total) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
     return AGB_E_WORKSPACE;

@@ -46,6 +46,20 @@ class DamsmConfig:
     max_words: Optional[int] = None
 
 
+def resolve_math(math, img_features=None, words_emb=None, gamma1: float = 4.0) -> int:
+    """name -> enum of include/attngan_b200.h.  "auto": the split-precision tensor-core path when the shapes are
+    inside its compiled range (and gamma1 inside fp16's range), else the fp32 CUDA-core path.  Both are native
+    kernels of this library; the choice is a host-side query (agb_damsm_supported), no data is touched."""
+    if math != "auto":
+        return native.MATH_NAMES[math]
+    if img_features is None or words_emb is None or not native.lib().agb_has_tcgen05() or gamma1 > 11.0:
+        return native.AGB_MATH_FP32
+    D, T = int(words_emb.shape[1]), int(words_emb.shape[2])
+    R = int(img_features.shape[2]) * int(img_features.shape[3]) if img_features.dim() == 4 else int(img_features.shape[2])
+    ok = native.lib().agb_damsm_supported(T, D, R, native.AGB_MATH_TC_F16X2)
+    return native.AGB_MATH_TC_F16X2 if ok else native.AGB_MATH_FP32
+
+
 def _world(group) -> int:
     return 1 if group is None else dist.get_world_size(group)
 

@@ -7,7 +7,13 @@ mask (:44-47,88-95).  The B-iteration Python loop and its ~14k ATen launches are
 native DAMSM kernels (forward and hand-written backward).
 
 Extra keyword-only options (all default to the reference behaviour):
-  math           "fp32" (CUDA cores, 1e-5 parity) | "f16" | "bf16" (tcgen05 tensor cores)
+  math           "auto" (default): "f16x2" when the shape is inside the tensor-core kernels' range (D = 256,
+                 T <= 32, <= 320 regions), else "fp32"
+                 "f16x2"  tcgen05, split-precision forward (loss within 1e-4 of the reference on any batch),
+                          fp16 backward
+                 "f16" | "bf16"  tcgen05, plain 16-bit operands: the fastest; loss within 1e-4 at training batch
+                          sizes (>= 48), ~5e-4 on tiny well-separated batches
+                 "fp32"   CUDA cores, 1e-5 parity, any D <= 256
   process_group  torch.distributed group: shard the batch over its ranks (negatives span the
                  global batch; see losses/damsm_core.py)
   att_maps       "list" (reference: list of [1, L_i, 17, 17]; needs cap_lens on the host)
@@ -20,13 +26,13 @@ from __future__ import annotations
 import torch
 
 from ..agb_native import native
-from .damsm_core import DamsmConfig, split_att_maps, words_loss
+from .damsm_core import DamsmConfig, resolve_math, split_att_maps, words_loss
 
 
 class WordsLoss:
     """Loss between words and images"""
 
-    def __init__(self, device, gamma1=4.0, gamma2=5.0, gamma3=10.0, wlambda=5.0, *, math="fp32",
+    def __init__(self, device, gamma1=4.0, gamma2=5.0, gamma3=10.0, wlambda=5.0, *, math="auto",
                  process_group=None, att_maps="list", max_words=None):
         self.device = device
         self.gamma1 = gamma1
@@ -46,9 +52,10 @@ class WordsLoss:
         w2 = torch.norm(x2, 2, dim)
         return (w12 / (w1 * w2).clamp(min=eps)).squeeze()
 
-    def _config(self) -> DamsmConfig:
+    def _config(self, img_features=None, words_emb=None) -> DamsmConfig:
         return DamsmConfig(gamma1=float(self.gamma1), gamma2=float(self.gamma2), gamma3=float(self.gamma3),
-                           lam=float(self.wlambda), eps=1e-8, math=native.MATH_NAMES[self.math],
+                           lam=float(self.wlambda), eps=1e-8,
+                           math=resolve_math(self.math, img_features, words_emb, float(self.gamma1)),
                            group=self.process_group, want_att=self.att_maps is not None,
                            max_words=self.max_words)
 
@@ -62,7 +69,7 @@ class WordsLoss:
             class_ids: (batch,) numpy array or None
         Returns (loss, att_maps)
         """
-        cfg = self._config()
+        cfg = self._config(img_features, words_emb)
         loss, att = words_loss(img_features, words_emb, labels, cap_lens, class_ids, cfg)
         ih, iw = img_features.shape[2], img_features.shape[3]
         if self.att_maps == "list":

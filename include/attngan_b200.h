@@ -37,6 +37,10 @@ enum agb_math {
   AGB_MATH_FP32 = 0,    /* CUDA-core fp32 (bit-for-bit deterministic forward, 1e-6 parity)      */
   AGB_MATH_TC_F16 = 1,  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM (default)   */
   AGB_MATH_TC_BF16 = 2, /* tcgen05 kind::f16, bf16 operands                                      */
+  /* split precision: every operand of the FORWARD enters the tensor core as hi + lo (two fp16 values) and the
+   * partial products accumulate in fp32, so similarities and losses are as accurate as fp32 arithmetic (1e-4
+   * on the loss for any batch, incl. the reference-derived fixtures); the backward runs the fp16 kernels. */
+  AGB_MATH_TC_F16X2 = 3,
   /* flag, OR-ed into `math` of agb_damsm_fwd by a caller that will run agb_damsm_bwd on the same
    * workspace (ws_from_fwd = 2): the tensor-core forward then also saves the normalised context
    * vectors and their statistics in the workspace and the backward does not recompute them.

@@ -47,7 +47,7 @@ def _fwd_bwd(ops, native, img3, wrd, l32, dm, math, need_dwords=True):
     return m, dimg, dwords
 
 
-@pytest.mark.parametrize("math", ["f16", "bf16"])
+@pytest.mark.parametrize("math", ["f16", "bf16", "f16x2"])
 @pytest.mark.parametrize("chunk_mb,min_chunks", [(11, 6), (22, 3), (33, 2)])
 def test_multi_chunk_backward_matches_single_chunk_fp32_and_oracle(agb, chunk_budget, math, chunk_mb, min_chunks):
     """B = 64 (tile staging = 64*128*1284 B = 10.5 MB per word tile; 11 tiles at most, 6-7 in use):
@@ -66,7 +66,7 @@ def test_multi_chunk_backward_matches_single_chunk_fp32_and_oracle(agb, chunk_bu
     chunk_budget(16384)                                   # single chunk
     m1, dimg1, dw1 = _fwd_bwd(ops, native, img3, wd, l32, dm, mode)
     chunk_budget(chunk_mb)
-    nt_max = (B + 5) // 6
+    nt_max = (B + 5) // 6                                 # 6 captions of T = 18 always fit a tile (3 per half tile)
     tile_mb = B * 128 * (320 * 2 * 2 + 4) / 2 ** 20
     ct = max(1, int(chunk_mb // tile_mb))
     assert (nt_max + ct - 1) // ct >= min_chunks, "the budget does not force the intended number of chunks"

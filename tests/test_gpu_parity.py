@@ -292,7 +292,7 @@ def test_damsm_fp32_matches_oracle_seeded(agb, B, T, full, ncls, trained):
     wd = wrd.cuda().requires_grad_(True)          # transposed view of [B,T,D]
     cn = cnn.cuda().requires_grad_(True)
     rn = rnn.cuda().requires_grad_(True)
-    wl, _ = agb.WordsLoss("cuda").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
+    wl, _ = agb.WordsLoss("cuda", math="fp32").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
     sl = agb.SentenceLoss("cuda").get_loss(cn, rn, labels.cuda(), cls)
     assert abs(wl.item() - wl0) <= 1e-5 * abs(wl0)
     assert abs(sl.item() - sl0) <= 1e-5 * abs(sl0)
@@ -308,7 +308,7 @@ def test_damsm_frozen_text_encoder_skips_dwords(agb):
     img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(6, T=9, D=64, hw=6, seed=4)
     _, _, dc0, _, _, _ = _oracle_damsm(img, wrd, cnn, rnn, labels, lens, cls)
     im = img.cuda().requires_grad_(True)
-    wl, _ = agb.WordsLoss("cuda").get_loss(im, wrd.cuda(), labels.cuda(), lens.cuda(), cls)
+    wl, _ = agb.WordsLoss("cuda", math="fp32").get_loss(im, wrd.cuda(), labels.cuda(), lens.cuda(), cls)
     wl.backward()
     assert_rel(im.grad, dc0, 1e-4)
 
@@ -367,13 +367,13 @@ def test_damsm_edge_cases(agb):
     wl0, sl0, dc0, dw0, _, _ = _oracle_damsm(img, wrd, cnn, rnn, labels, lens, cls)
     im = img.cuda().requires_grad_(True)
     wd = wrd.cuda().requires_grad_(True)
-    wl, maps = agb.WordsLoss("cuda").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
+    wl, maps = agb.WordsLoss("cuda", math="fp32").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
     assert [m.shape[1] for m in maps] == [1, 6, 2, 1]
     assert abs(wl.item() - wl0) <= 1e-5 * max(abs(wl0), 1e-6) + 1e-7
     wl.backward()
     assert_rel(im.grad, dc0, 1e-4) if np.abs(dc0).max() > 0 else None
     img1, wrd1, _, _, labels1, lens1, _ = rp.synth_damsm(1, T=4, D=32, hw=3, seed=1)
-    wl1, _ = agb.WordsLoss("cuda").get_loss(img1.cuda(), wrd1.cuda(), labels1.cuda(), lens1.cuda(), None)
+    wl1, _ = agb.WordsLoss("cuda", math="fp32").get_loss(img1.cuda(), wrd1.cuda(), labels1.cuda(), lens1.cuda(), None)
     assert wl1.item() == 0.0                                # a 1x1 cross-entropy
 
 

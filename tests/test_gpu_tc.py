@@ -92,7 +92,7 @@ def _rel(x, ref):
     return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30)
 
 
-@pytest.mark.parametrize("math,tol", [("f16", 2e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("math,tol", [("f16", 2e-3), ("bf16", 2e-2), ("f16x2", 2e-5)])
 @pytest.mark.parametrize("B,full,trained", [(7, True, False), (16, False, False), (48, False, 0.12), (130, False, False)])
 def test_tc_similarity_matrix_matches_oracle(agb, math, tol, B, full, trained):
     """m[b,i] = log sum_t exp(gamma2 cos) for every pair, against the fp64 closed form"""
@@ -112,22 +112,27 @@ def test_tc_similarity_matrix_matches_oracle(agb, math, tol, B, full, trained):
     assert (m - m32).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("math", ["f16x2", "auto", "f16"])
 @pytest.mark.parametrize("name", ["damsm_real_cls", "damsm_real_trained"])
-def test_tc_losses_match_reference_golden(agb, name):
+def test_tc_losses_match_reference_golden(agb, name, math):
+    """the reference-derived fixtures (B = 3, D = 256) on the tensor-core paths.  north_star: loss within 1e-4.
+    "f16x2" (split-precision forward; what the drop-in default "auto" resolves to at these shapes) meets it on
+    every fixture.  Plain "f16" cannot at B = 3: each of its four fp16 operand roundings moves this loss by ~1e-4
+    (scripts/emulate_rounding.py reproduces the 4.7e-4 in numpy); its bound here is 1e-3, and 1e-4 from
+    training batch sizes on (test_tc_words_loss_cfg2, tests/test_gpu_chunks.py)."""
     g = load_golden(name)
     cls = g["class_ids"] if bool(g["has_class_ids"]) else None
     dev = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)  # noqa: E731
     im = dev(g["img"]).requires_grad_(True)
     wt = dev(g["words"].transpose(0, 2, 1)).requires_grad_(True)
     cn, rn = dev(g["cnn"]).requires_grad_(True), dev(g["rnn"]).requires_grad_(True)
-    L = agb.DAMSMLoss("cuda", math="f16")
+    L = agb.DAMSMLoss("cuda", math=math)
     wl, sl, maps = L.get_losses(im, cn, wt.transpose(1, 2), rn, dev(g["labels"], torch.int64),
                                 dev(g["cap_lens"], torch.int64), cls)
-    # B = 3: no averaging over pairs, and each of the four fp16 operand roundings (scores GEMM,
-    # e = exp(gamma1 alpha), context GEMM, cosine numerator) costs ~1e-4 on the trained-like case
-    # (measured by emulating the roundings in numpy: 4.7e-4 in total, which is what the kernel
-    # gives).  1e-4 holds at BASELINE batch sizes (test_tc_words_loss_cfg2) and in fp32 mode.
-    assert abs(wl.item() - float(g["wloss_f64"])) <= 1e-3 * abs(float(g["wloss_f64"]))
+    loss_tol = 1e-3 if math == "f16" else 1e-4
+    assert abs(wl.item() - float(g["wloss_f64"])) <= loss_tol * abs(float(g["wloss_f64"])), (wl.item(), float(g["wloss_f64"]))
+    if math != "f16":      # the split forward is fp32-accurate: an order of magnitude inside the bound
+        assert abs(wl.item() - float(g["wloss_f64"])) <= 2e-5 * abs(float(g["wloss_f64"]))
     assert abs(sl.item() - float(g["sloss_f64"])) <= 1e-4 * abs(float(g["sloss_f64"]))
     for i, m in enumerate(maps):
         Li = int(g["cap_lens"][i])
@@ -135,6 +140,73 @@ def test_tc_losses_match_reference_golden(agb, name):
     (wl + sl).backward()
     assert _rel(im.grad, g["dimg"]) < 5e-3
     assert _rel(wt.grad.transpose(1, 2), g["dwords"]) < 5e-3
+
+
+def test_drop_in_default_is_the_tensor_core_path(agb):
+    """WordsLoss(device) without options runs tcgen05 kernels where the shape allows and the fp32 kernels elsewhere"""
+    from attention_gan_b200.agb_native import native
+    from attention_gan_b200.losses.damsm_core import resolve_math
+    assert agb.WordsLoss("cuda").math == "auto"
+    assert resolve_math("auto", torch.empty(4, 256, 17, 17), torch.empty(4, 256, 18)) == native.AGB_MATH_TC_F16X2
+    assert resolve_math("auto", torch.empty(4, 32, 5, 5), torch.empty(4, 32, 7)) == native.AGB_MATH_FP32
+    assert resolve_math("auto", torch.empty(4, 256, 17, 17), torch.empty(4, 256, 40)) == native.AGB_MATH_FP32
+    lib = native.lib()
+    n0 = lib.agb_launch_count()
+    lib.agb_prof_enable(1)
+    img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(8, seed=1)
+    wl, _ = agb.WordsLoss("cuda").get_loss(img.cuda(), wrd.cuda(), labels.cuda(), lens.cuda(), cls)
+    torch.cuda.synchronize()
+    import ctypes
+    ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
+    lib.agb_prof_read(2, ctypes.byref(ms), ctypes.byref(n))       # tag 2 = tcgen05 DAMSM forward pair kernel
+    lib.agb_prof_enable(0)
+    assert n.value == 1 and lib.agb_launch_count() > n0
+
+
+@pytest.mark.parametrize("B,T,hw", [(48, 18, 17), (33, 5, 17), (10, 7, 13), (6, 32, 16), (9, 18, 8), (130, 18, 17)])
+def test_split_precision_loss_and_gradients(agb, B, T, hw):
+    """AGB_MATH_TC_F16X2 end to end: loss at fp32 accuracy (1e-5 here, bound 1e-4), gradients from the fp16
+    backward on the SAME workspace (half-tile packing, saved context vectors), class-id mask, odd region counts"""
+    img, wrd, cnn, rnn, labels, lens, cls = rp.synth_damsm(B, T=T, hw=hw, seed=900 + B + T, n_classes=max(2, B // 4),
+                                                           trained_like=0.1 if B < 40 else False)
+    nb = B if B <= 48 else 24
+    R = hw * hw
+    if B <= 48:
+        wl0, _, dc0, dw0 = cf.words_loss_fwd_bwd(img.numpy().reshape(B, 256, R), wrd.numpy(), labels.numpy(),
+                                                 lens.numpy(), cls)
+    im = img.cuda().requires_grad_(True)
+    wd = wrd.cuda().requires_grad_(True)
+    wl, maps = agb.WordsLoss("cuda", math="f16x2").get_loss(im, wd, labels.cuda(), lens.cuda(), cls)
+    wl.backward()
+    if B <= 48:
+        assert abs(wl.item() - wl0) <= 1e-5 * abs(wl0), (wl.item(), wl0)
+        assert _rel(im.grad, dc0.reshape(img.shape)) < 5e-3
+        assert _rel(wd.grad, dw0) < 5e-3
+    else:                      # large batch: against the native fp32 path (oracle-pinned)
+        im2 = img.cuda().requires_grad_(True)
+        wd2 = wrd.cuda().requires_grad_(True)
+        wl2, _ = agb.WordsLoss("cuda", math="fp32").get_loss(im2, wd2, labels.cuda(), lens.cuda(), cls)
+        wl2.backward()
+        assert abs(wl.item() - wl2.item()) <= 1e-5 * abs(wl2.item()), (wl.item(), wl2.item())
+        assert _rel(im.grad, im2.grad) < 5e-3 and _rel(wd.grad, wd2.grad) < 5e-3
+    assert maps[0].shape == (1, int(lens[0]), hw, hw)
+
+
+def test_split_precision_row_blocks_equal_full_matrix(agb):
+    """sharding identity in split precision: row blocks with row_offset reproduce the full matrix bit for bit"""
+    from attention_gan_b200.agb_native import native, ops
+    B = 40
+    img, wrd, _, _, _, lens, _ = rp.synth_damsm(B, seed=55)
+    lens[:6] = torch.tensor([1, 18, 1, 17, 18, 2])
+    img3 = img.cuda().reshape(B, 256, -1).contiguous()
+    l32 = lens.cuda().to(torch.int32)
+    m, _, _ = ops.damsm_fwd(img3, wrd.cuda(), l32, 4.0, 5.0, 1e-8, 0, False, native.AGB_MATH_TC_F16X2)
+    for k in range(4):
+        mk, _, _ = ops.damsm_fwd(img3[10 * k:10 * k + 10].contiguous(), wrd.cuda(), l32, 4.0, 5.0, 1e-8, 10 * k, False,
+                                 native.AGB_MATH_TC_F16X2)
+        assert torch.equal(mk, m[10 * k:10 * k + 10])
+    ref = cf.words_similarity_fwd(img.numpy().reshape(B, 256, -1)[:8], wrd.numpy(), lens.numpy())
+    assert np.abs(m[:8].double().cpu().numpy() - ref).max() < 2e-5
 
 
 @pytest.mark.parametrize("math", ["f16", "bf16"])

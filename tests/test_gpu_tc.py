@@ -88,7 +88,7 @@ from oracle import ref_port as rp         # noqa: E402
 
 def _rel(x, ref):
     x = x.detach().double().cpu().numpy() if torch.is_tensor(x) else np.asarray(x, np.float64)
-    ref = np.asarray(ref, np.float64)
+    ref = ref.detach().double().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref, np.float64)
     return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30)
 
 

@@ -15,6 +15,10 @@ BASELINE.json configs[3] -- the configuration the headline metric is quoted on:
   cfg3   generator word attention forward+backward, bf16, batch 64, stages 64x64 + 128x128 + 256x256 (configs[2])
   cfg5   long-caption stress: T=64 words, 256x256, bf16, batch 256 split over the ranks (configs[4]; 32 per GPU)
   cfg1   attention fp32, batch 16, 64x64 (configs[0])
+  cfg4step  the WHOLE pretraining step of configs[3] (reference pretrain_damsm.py:110-134): synthetic 7-token bedroom
+         captions -> LSTM text encoder + the two trainable CNN heads (on synthetic Inception features) -> both
+         losses -> backward -> clip_grad_norm_(RNN, 0.25) -> Adam; global batch 2048 sharded over the ranks
+         (attention-gan_b200/pretrain/); at N=1 a batch-256 version runs as a secondary measurement
 
 At N=1 the default run also measures cfg2, cfg3 and one GPU's share of cfg5 and reports them under "secondary"
 in the same JSON line (pairs/s, pixels/s, HBM fraction).
@@ -216,8 +220,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     wl = args.workload
-    if wl in ("cfg2", "cfg4"):
-        Bg = args.batch or CFG_BATCH[wl]
+    if wl in ("cfg2", "cfg4", "cfg4step"):
+        Bg = args.batch or CFG_BATCH.get(wl, 2048)
         B = min(Bg, 48 if wl == "cfg2" else 96)
         step, units = ref_damsm_step(B, Bg)
         metric, unit = METRIC_DAMSM, "pairs/s"
@@ -237,8 +241,8 @@ def run_reference(args):
     v = units / sec
     line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong" if wl in ("cfg4", "cfg5") else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": workload_name(wl, args.batch)},
+            "scaling": "strong" if wl in ("cfg4", "cfg5", "cfg4step") else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name("cfg4" if wl == "cfg4step" else wl, args.batch)},
             "cpu_baseline": {"value": v, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -403,7 +407,45 @@ def damsm_workload(env: Env, wl, Bg, math, steps, warmup, sample_clocks):
     m = env.measure(make_dev, step_dev, step_e2e, tags, steps, warmup, sample_clocks)
     m.update(units=Bl * Bg, total_units=Bg * Bg, h2d=int(h2d), d2h=8, mean_len=mean_len, tc=tc,
              flop_unit=2.0 * R_ * mean_len * D_, metric=METRIC_DAMSM, unit="pairs/s",
-             dtype={"fp32": "f32", "f16": "f16", "bf16": "bf16"}[math], math=math)
+             dtype={"fp32": "f32", "f16": "f16", "bf16": "bf16", "f16x2": "f16"}[math], math=math)
+    return m
+
+
+def pretrain_workload(env: Env, Bg, math, steps, warmup, sample_clocks):
+    """the whole DAMSM pretraining step on synthetic bedroom captions + synthetic Inception features"""
+    torch, dev, world, rank = env.torch, env.dev, env.world, env.rank
+    from attention_gan_b200.pretrain import DamsmPretrainStep, SyntheticBedroomCaptions
+    assert Bg % world == 0
+    Bl = Bg // world
+    sl = slice(rank * Bl, rank * Bl + Bl)
+    data = SyntheticBedroomCaptions(Bg, seed=0)             # k = 7..500 hierarchy, 7-token captions, <= 990 words
+    g = torch.Generator().manual_seed(0)
+    caps_h = data.captions[sl].contiguous().pin_memory()
+    lens_h = data.lengths[sl].to(torch.int32).contiguous().pin_memory()
+    cls_h = data.class_ids[sl].to(torch.int32).contiguous().pin_memory()
+    m6e_h = (torch.randn(Bg, 768, 17, 17, generator=g)[sl] * 0.5).contiguous().pin_memory()
+    pool_h = (torch.randn(Bg, 2048, generator=g)[sl] * 0.5).contiguous().pin_memory()
+    labels = torch.arange(Bl, device=dev)
+    st = DamsmPretrainStep(data.vocab_size, dev, math=math, process_group=env.group, fixed_length=True, max_words=7)
+    out_h = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (caps_h, lens_h, cls_h, m6e_h, pool_h))
+
+    def make_dev():
+        return [caps_h.to(dev), lens_h.to(dev), cls_h.to(dev), m6e_h.to(dev), pool_h.to(dev)]
+
+    def step_dev(ts):
+        return st.step(ts[0], ts[1], ts[2], ts[3], ts[4], labels)
+
+    def step_e2e():
+        ts = [t.to(dev, non_blocking=True) for t in (caps_h, lens_h, cls_h, m6e_h, pool_h)]
+        loss = st.step(ts[0], ts[1], ts[2], ts[3], ts[4], labels)
+        out_h.copy_(loss.reshape(1), non_blocking=True)
+
+    tc = math != "fp32"
+    m = env.measure(make_dev, step_dev, step_e2e, list(DAMSM_KERNELS) if tc else [1], steps, warmup, sample_clocks)
+    m.update(units=Bl * Bg, total_units=Bg * Bg, h2d=int(h2d), d2h=4, mean_len=7.0, tc=tc,
+             flop_unit=2.0 * R_ * 7.0 * D_, metric="damsm_pretrain_step_pairs_per_sec", unit="pairs/s",
+             dtype={"fp32": "f32", "f16": "f16", "bf16": "bf16", "f16x2": "f16"}[math], math=math)
     return m
 
 
@@ -549,8 +591,14 @@ def run_native(args):
     torch = env.torch
     peaks = load_peaks()
     wl = args.workload
-    damsm = wl in ("cfg2", "cfg4")
-    if damsm:
+    damsm = wl in ("cfg2", "cfg4", "cfg4step")
+    if wl == "cfg4step":
+        Bg = args.batch or 2048
+        m = pretrain_workload(env, Bg, args.math, args.steps, args.warmup, True)
+        roof = damsm_roofline(m, peaks, long_step=m["value"] > 2e-3)
+        name = (f"cfg4step: DAMSM pretraining step (text LSTM + CNN heads + WordsLoss + SentenceLoss + backward + clip + "
+                f"Adam), synthetic 7-token bedroom captions (k=7..500 hierarchy, <=990 words), global batch {Bg}")
+    elif damsm:
         Bg = args.batch or CFG_BATCH[wl]
         m = damsm_workload(env, wl, Bg, args.math, args.steps, args.warmup, True)
         roof = damsm_roofline(m, peaks, long_step=m["value"] > 2e-3)
@@ -563,11 +611,23 @@ def run_native(args):
     secondary = {}
     if env.world == 1 and args.secondary and not (args.batch or args.hw):
         ssteps, swarm = min(args.steps, 20), 3
-        for w2 in ("cfg2", "cfg3", "cfg5"):
+        for w2 in ("cfg2", "cfg3", "cfg5", "cfg4_f16x2", "pretrain_step_b256"):
             if w2 == wl:
                 continue
             try:
-                if w2 == "cfg2":
+                if w2 == "cfg4_f16x2":
+                    if wl != "cfg4" or args.math == "f16x2":
+                        continue
+                    m2 = damsm_workload(env, "cfg4", CFG_BATCH["cfg4"], "f16x2", 5, swarm, False)
+                    secondary[w2] = summary(m2, damsm_roofline(m2, peaks, long_step=True),
+                                            workload_name("cfg4") + "; math=f16x2 (split-precision forward: loss within "
+                                            "1e-4 of the reference on every fixture)")
+                elif w2 == "pretrain_step_b256":
+                    m2 = pretrain_workload(env, 256, args.math, ssteps, swarm, False)
+                    secondary[w2] = summary(m2, damsm_roofline(m2, peaks, long_step=False),
+                                            "whole DAMSM pretraining step (pretrain_damsm.py:110-134), synthetic bedroom "
+                                            "captions (7 tokens), batch 256 on one GPU")
+                elif w2 == "cfg2":
                     m2 = damsm_workload(env, w2, CFG_BATCH[w2], args.math, ssteps, swarm, False)
                     secondary[w2] = summary(m2, damsm_roofline(m2, peaks, long_step=False), workload_name(w2))
                 else:
@@ -589,7 +649,7 @@ def run_native(args):
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         if damsm:
-            cstep, cunits = ref_damsm_step(48, CFG_BATCH["cfg4"] if wl == "cfg4" else 48)
+            cstep, cunits = ref_damsm_step(48, CFG_BATCH["cfg4"] if wl != "cfg2" else 48)
             csample = ("oracle/ref_port.py WordsLoss+SentenceLoss fwd+bwd on the first 48 samples of the workload's batch "
                        "(48x48 pairs per step), fp32, 3 steps after 1 warm-up")
             gstep, gunits = ref_damsm_step(128, max(128, CFG_BATCH.get(wl, 128)), device=env.dev)
@@ -611,7 +671,7 @@ def run_native(args):
     sec, sec2 = m["value"], m["e2e"]
     line = {"metric": m["metric"], "value": m["total_units"] / sec, "unit": m["unit"], "n_gpus": env.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong" if wl in ("cfg4", "cfg5") else "weak", "vs_baseline": None, "dtype": m["dtype"],
+            "scaling": "strong" if wl in ("cfg4", "cfg5", "cfg4step") else "weak", "vs_baseline": None, "dtype": m["dtype"],
             "data": "synthetic", "config": {"workload": name},
             "method": {"math": args.math if damsm else None,
                        "l2": "256 MiB write between timed iterations (outside the events)",
@@ -640,8 +700,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
-    ap.add_argument("--math", default=None, choices=["fp32", "f16", "bf16"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "cfg4step"])
+    ap.add_argument("--math", default=None, choices=["fp32", "f16", "bf16", "f16x2"])
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--hw", type=int, default=None, help="attention workloads: a single feature-map side instead of the config's stages")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")

@@ -336,6 +336,7 @@ class Env:
         g = self.graphed(lambda: step_dev(ts))
         if g is None and sampler:
             sampler.start()                       # no graph (torchrun / --no-graph): the eager timing IS the value
+        step_dev(ts)                              # untimed: re-grows the allocator pool emptied above (cudaMalloc of the workspace)
         out["eager"] = self.timed(lambda: step_dev(ts), steps)
         if g is not None:
             if sampler:

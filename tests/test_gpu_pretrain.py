@@ -29,7 +29,7 @@ def test_pretrain_step_matches_oracle_step(math, ptol):
     B = 16
     d, caps, lens, cls, m6e, pooled = _batch(B, seed=11)
     st = DamsmPretrainStep(d.vocab_size, "cuda", math=math, seed=5)
-    st.rnn.eval()                                           # dropout off: both arms must see the same activations
+    st.rnn.dropout.p = 0.0                                  # dropout off (train mode stays: cuDNN LSTM backward needs it)
     rnn0, heads0 = copy.deepcopy(st.rnn), copy.deepcopy(st.heads)
     params0 = list(rnn0.parameters()) + list(heads0.parameters())
     opt0 = torch.optim.Adam(params0, lr=2e-3, betas=(0.5, 0.999))
@@ -66,7 +66,7 @@ def test_graphed_pretrain_step_equals_eager():
     eager = DamsmPretrainStep(d.vocab_size, "cuda", math="f16", seed=9)
     graphed = DamsmPretrainStep(d.vocab_size, "cuda", math="f16", seed=9)
     for s in (eager, graphed):
-        s.rnn.eval()
+        s.rnn.dropout.p = 0.0
     static = [t.clone() for t in (caps, lens, cls_dev, m6e, pooled)]
     snap = copy.deepcopy((graphed.rnn.state_dict(), graphed.heads.state_dict(), graphed.optimizer.state_dict()))
     step = agb.GraphedStep(lambda: graphed.step(static[0], static[1], static[2], static[3], static[4], labels))

@@ -28,6 +28,8 @@ struct Options {
   long long damsm_save_bytes;    // budget of what the training forward saves            (AGB_DAMSM_SAVE_MB)
   int damsm_bwd;                 // 2 = always the recomputing backward                  (AGB_DAMSM_BWD)
   int damsm_uniform_split;       // != 0: equal item counts per CTA, not equal cost      (AGB_DAMSM_UNIFORM_SPLIT)
+  int damsm_img_block;           // images per L2 block of the pair kernels, 0 = off     (AGB_DAMSM_IMG_BLOCK)
+  int damsm_dw_splits;           // image slices of the d words reduction                (AGB_DAMSM_DW_SPLITS)
   int attn_fwd_stages, attn_fwd_ctas, attn_bwd_stages, attn_bwd_ctas;   // tuning knobs  (AGB_ATTN_*), 0 = automatic
 };
 const Options& options();

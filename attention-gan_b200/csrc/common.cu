@@ -57,6 +57,8 @@ static void load_options() {
   g_opt.damsm_save_bytes = env_ll("AGB_DAMSM_SAVE_MB", 65536) << 20;
   g_opt.damsm_bwd = (int)env_ll("AGB_DAMSM_BWD", 0);
   g_opt.damsm_uniform_split = (int)env_ll("AGB_DAMSM_UNIFORM_SPLIT", 0);
+  g_opt.damsm_img_block = (int)env_ll("AGB_DAMSM_IMG_BLOCK", 0);
+  g_opt.damsm_dw_splits = (int)env_ll("AGB_DAMSM_DW_SPLITS", 16);
   g_opt.attn_fwd_stages = (int)env_ll("AGB_ATTN_FWD_STAGES", 0);
   g_opt.attn_fwd_ctas = (int)env_ll("AGB_ATTN_FWD_CTAS", 0);
   g_opt.attn_bwd_stages = (int)env_ll("AGB_ATTN_BWD_STAGES", 0);
@@ -150,6 +152,8 @@ extern "C" int agb_set_option(const char* name, long long value) {
   else if (n == "damsm_save_mb") o.damsm_save_bytes = value << 20;
   else if (n == "damsm_bwd") o.damsm_bwd = (int)value;
   else if (n == "damsm_uniform_split") o.damsm_uniform_split = (int)value;
+  else if (n == "damsm_img_block") o.damsm_img_block = (int)value;
+  else if (n == "damsm_dw_splits") o.damsm_dw_splits = (int)value;
   else if (n == "attn_fwd_stages") o.attn_fwd_stages = (int)value;
   else if (n == "attn_fwd_ctas") o.attn_fwd_ctas = (int)value;
   else if (n == "attn_bwd_stages") o.attn_bwd_stages = (int)value;

@@ -19,7 +19,8 @@
 //
 // HBM layout of the pre-packed operands (written by the pack kernels below, 16-bit):
 //   Wh [tiles*128, 256]   packed caption words, K-major rows; unused rows are zero
-//   Ct [Bi*384, 256]      regions as rows (M operand of GEMM1), rows >= R zero
+//   Ct [Bi*384, 256]      regions as rows (M operand of GEMM1), rows >= R zero, except that rows 320.. repeat the
+//                         regions 256..R-1 of the remainder tile (work sharing between the TMEM lane quarters)
 //   Ck [Bi*256, 320]      features as rows (N operand of GEMM2), columns >= R zero
 #include <algorithm>
 #include <type_traits>
@@ -176,8 +177,18 @@ __global__ void pack_img_kernel_tc(const float* __restrict__ img, T16* __restric
     const int r = r0 + k, d = d0 + tx;
     const float v = tile[tx][k];
     const T16 h = cvt16<T16>(v);
-    Ct[((size_t)b * kRRows + r) * kD + d] = h;
-    if (Ctl) Ctl[((size_t)b * kRRows + r) * kD + d] = cvt16<T16>(v - to_f32(h));
+    const T16 l = cvt16<T16>(v - to_f32(h));
+    const bool dup_target = r >= 320 && r - 64 < R;       // written below by the block that owns region r - 64
+    if (!dup_target) {
+      Ct[((size_t)b * kRRows + r) * kD + d] = h;
+      if (Ctl) Ctl[((size_t)b * kRRows + r) * kD + d] = l;
+    }
+    // the regions of the third (remainder) tile once more in its lanes 64..127 (rows 320..): the pair kernels let
+    // lane quarters 2, 3 work on them with the other half of the captions (see `dup` in the epilogues)
+    if (r >= 256 && r < R && r + 64 < kRRows) {
+      Ct[((size_t)b * kRRows + r + 64) * kD + d] = h;
+      if (Ctl) Ctl[((size_t)b * kRRows + r + 64) * kD + d] = l;
+    }
   }
 }
 
@@ -263,6 +274,8 @@ struct FwdParams {
   const int32_t* cap_lens;
   const int32_t* tile_cpre;   // [ntiles + 1] exclusive prefix of the per-item cost of each word tile
   int uniform_split;          // != 0: equal item counts per CTA instead of equal cost (option damsm_uniform_split, for A/B timing)
+  int dup_rem;                // != 0: region tile 2 carries its regions twice (lanes 0..63 and 64..127, see pack_img_kernel_tc)
+  int img_block;              // > 0: item order (image block, word tile, image) with this many images per block (item_pos)
   const float* pn;
   float* m_out;
   int Bi, Bc, T, R;
@@ -337,7 +350,7 @@ static TcPlan make_tc_plan(int Bi, int Bc, int T, int D, int R, bool split) {
   if (ct < 1) ct = 1;
   if (ct > (size_t)p.nt_max) ct = p.nt_max;
   p.ct = (int)ct;
-  p.splits = std::min(Bi, 16);
+  p.splits = std::max(1, std::min(Bi, opt.damsm_dw_splits));
   const size_t rows = (size_t)Bi * ct * kTileN;
   p.off_E16 = take(rows * kRCols * 2);
   p.off_dV16 = p.save ? p.off_E16 : take(rows * kD * 2);
@@ -425,6 +438,8 @@ static int launch_fwd(const Packed& pk, const int32_t* cap_lens, int Bi, int Bc,
   p.tile_first = pk.tfirst; p.tile_ncap = pk.tncap; p.ntiles = pk.ntiles; p.cap_row = pk.cap_row; p.cap_lens = cap_lens;
   p.tile_cpre = pk.tcpre;
   p.uniform_split = options().damsm_uniform_split;
+  p.img_block = options().damsm_img_block;
+  p.dup_rem = R > 256 ? 1 : 0;
   p.pn = pk.pn; p.m_out = m_out; p.Bi = Bi; p.Bc = Bc; p.T = T; p.R = R;
   p.scale_log2 = kLog2e / sqrtf((float)kD);
   p.g1_log2 = gamma1 * kLog2e;

@@ -67,6 +67,8 @@ int agb_has_tcgen05(void);
  *   "damsm_save_mb"   (AGB_DAMSM_SAVE_MB, 65536)   budget for the context vectors the training forward saves;
  *                     above it the backward recomputes them (damsm_bwd2_kernel)
  *   "damsm_bwd"       (AGB_DAMSM_BWD, 0)           2 = always the recomputing backward
+ *   "damsm_img_block" (AGB_DAMSM_IMG_BLOCK)      images per L2 block of the pair kernels' item order, 0 = off
+ *   "damsm_dw_splits" (AGB_DAMSM_DW_SPLITS, 16)  image slices of the d words reduction
  *   "damsm_uniform_split", "attn_fwd_stages", "attn_fwd_ctas", "attn_bwd_stages", "attn_bwd_ctas": kernel tuning
  * Set an option BEFORE querying a workspace size that depends on it and keep it unchanged between a forward and its
  * backward.  Returns 0, or AGB_E_BADARG for an unknown name. */

@@ -50,7 +50,7 @@ class HostPrefetcher:
             if self.free[k] is not None:
                 self.copy_stream.wait_event(self.free[k])     # the step that last read this set has finished
             for d, h in zip(self.sets[k], host_tensors):
-                d.copy_(h, non_blocking=True)
+                d.detach().copy_(h, non_blocking=True)        # (a consumer may have set requires_grad on the buffer)
                 self.bytes_copied += h.numel() * h.element_size()
             self.ready[k].record(self.copy_stream)
         self.queue.append(k)

@@ -474,8 +474,13 @@ def pretrain_workload(env: Env, Bg, math, steps, warmup, sample_clocks):
         loss = st.step(ts[0], ts[1], ts[2], ts[3], ts[4], labels)
         out_h.copy_(loss.reshape(1), non_blocking=True)
 
+    def run_on(ts):
+        loss = st.step(ts[0], ts[1], ts[2], ts[3], ts[4], labels)
+        out_h.copy_(loss.reshape(1), non_blocking=True)
+
     tc = math != "fp32"
-    m = env.measure(make_dev, step_dev, step_e2e, list(DAMSM_KERNELS) if tc else [1], steps, warmup, sample_clocks)
+    m = env.measure(make_dev, step_dev, step_e2e, list(DAMSM_KERNELS) if tc else [1], steps, warmup, sample_clocks,
+                    e2e_pipe=([caps_h, lens_h, cls_h, m6e_h, pool_h], run_on))
     m.update(units=Bl * Bg, total_units=Bg * Bg, h2d=int(h2d), d2h=4, mean_len=7.0, tc=tc,
              flop_unit=2.0 * R_ * 7.0 * D_, metric="damsm_pretrain_step_pairs_per_sec", unit="pairs/s",
              dtype={"fp32": "f32", "f16": "f16", "bf16": "bf16", "f16x2": "f16"}[math], math=math)
@@ -548,9 +553,22 @@ def attn_workload(env: Env, wl, batch, hw_only, steps, warmup, sample_clocks, lo
             ctx.backward(dctx)
             out_h[256 * i:256 * (i + 1)].copy_(im.grad.reshape(-1)[:256], non_blocking=True)   # a slice of every stage's result
 
+    def run_on(ts):
+        n = len(hws)
+        wd = ts[2 * n].requires_grad_(True)
+        wd.grad = None
+        for i, mod in enumerate(mods):
+            im = ts[i].requires_grad_(True)
+            im.grad = None
+            mod.conv1.weight.grad = None
+            ctx, attn = mod(im, wd.transpose(1, 2))
+            ctx.backward(ts[n + i])
+            out_h[256 * i:256 * (i + 1)].copy_(im.grad.reshape(-1)[:256], non_blocking=True)
+
     npix = sum(hw * hw for hw in hws)
     es = 4 if tdt == torch.float32 else 2
-    m = env.measure(make_dev, step_dev, step_e2e, [4, 5], steps, warmup, sample_clocks)
+    m = env.measure(make_dev, step_dev, step_e2e, [4, 5], steps, warmup, sample_clocks,
+                    e2e_pipe=([*img_h, *dctx_h, wrd_h], run_on))
     m.update(units=Bl * npix, total_units=B * npix, h2d=int(h2d), d2h=int(d2h), metric=METRIC_ATTN, unit="pixels/s",
              bytes_fwd=es * (2 * C + T), bytes_bwd=es * 3 * C, dtype="f32" if es == 4 else "bf16",
              io="fp32" if es == 4 else "bf16", B=B, T=T, C=C, hws=hws)

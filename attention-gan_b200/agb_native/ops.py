@@ -215,3 +215,37 @@ def func_attention_bwd(query, context, gamma1, scaled, dwc, dattn, need_dquery=T
                                         _p(dattn), _p(dq), _p(dc), _p(ws), ws.numel(), _stream(query))
     N.check(rc, "agb_func_attention_bwd")
     return dq, dc
+
+
+# ------------------------------------------------------------------------------------------------
+# region-feature head of the image encoder                reference networks/cnn_encoder.py:56,101
+# ------------------------------------------------------------------------------------------------
+def region_head_fwd(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """x [B,Cin,R] fp32 contiguous, weight [Cout,Cin] fp32 -> feat [B,Cout,R] fp32 (tcgen05, split precision)"""
+    require_cuda(x, weight)
+    B, Cin, R = x.shape
+    Cout = weight.shape[0]
+    nbytes = N.lib().agb_region_head_workspace_bytes(B, Cin, Cout, R)
+    if nbytes == 0:
+        raise N.NativeError(f"region head shape Cin={Cin} Cout={Cout} is unsupported (Cin % 64, Cout % 128)")
+    ws = _ws(nbytes, x.device)
+    feat = torch.empty((B, Cout, R), dtype=torch.float32, device=x.device)
+    rc = N.lib().agb_region_head_fwd(_p(x), _p(weight), _p(feat), _p(ws), ws.numel(), B, Cin, Cout, R, _stream(x))
+    N.check(rc, "agb_region_head_fwd")
+    return feat
+
+
+def region_head_bwd(x: torch.Tensor, weight: torch.Tensor, dfeat: torch.Tensor, need_dw: bool, need_dx: bool):
+    """Returns (dweight [Cout,Cin] or None, dx [B,Cin,R] or None)"""
+    require_cuda(x, weight, dfeat)
+    B, Cin, R = x.shape
+    Cout = weight.shape[0]
+    ws = _ws(N.lib().agb_region_head_workspace_bytes(B, Cin, Cout, R), x.device)
+    dw = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device) if need_dw else None
+    dx = torch.empty_like(x) if need_dx else None
+    if not (need_dw or need_dx):
+        return None, None
+    rc = N.lib().agb_region_head_bwd(_p(x), _p(weight), _p(dfeat), _p(dw), _p(dx), _p(ws), ws.numel(), B, Cin, Cout, R,
+                                     _stream(x))
+    N.check(rc, "agb_region_head_bwd")
+    return dw, dx

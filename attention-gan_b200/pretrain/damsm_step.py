@@ -28,6 +28,7 @@ from torch.nn.utils import clip_grad_norm_
 from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
 
 from ..losses.damsm_loss import DAMSMLoss
+from ..networks.region_head import _RegionHead
 
 
 class TextEncoder(nn.Module):
@@ -70,9 +71,10 @@ class TextEncoder(nn.Module):
 class RegionHeads(nn.Module):
     """the two trainable heads of the reference's CNNEncoder (cnn_encoder.py:54-64,98-102)"""
 
-    def __init__(self, out_dim: int = 256):
+    def __init__(self, out_dim: int = 256, native: bool = True):
         super().__init__()
         self.out_dim = out_dim
+        self.native = native           # emb_features on tcgen05 (networks/region_head.py) instead of an fp32 cuDNN conv
         self.emb_features = nn.Conv2d(768, out_dim, kernel_size=1, stride=1, padding=0, bias=False)   # Layers.conv1x1
         self.emb_cnn_code = nn.Linear(2048, out_dim)
         self.emb_features.weight.data.uniform_(-0.1, 0.1)                  # cnn_encoder.py:60-64
@@ -80,17 +82,19 @@ class RegionHeads(nn.Module):
 
     def forward(self, mixed_6e: torch.Tensor, pooled: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """mixed_6e [B,768,17,17], pooled [B,2048] -> (region features [B,256,17,17], cnn_code [B,256])"""
+        if self.native and mixed_6e.is_cuda:
+            return _RegionHead.apply(mixed_6e, self.emb_features.weight), self.emb_cnn_code(pooled)
         return self.emb_features(mixed_6e), self.emb_cnn_code(pooled)
 
 
 class DamsmPretrainStep:
     def __init__(self, vocab_size: int, device, emb_dim: int = 256, lr: float = 2e-3, rnn_grad_clip: float = 0.25,
                  math: str = "auto", process_group=None, fixed_length: bool = True, max_words: Optional[int] = None,
-                 seed: int = 0):
+                 seed: int = 0, native_head: bool = True):
         torch.manual_seed(seed)
         self.device = torch.device(device)
         self.rnn = TextEncoder(vocabsize=vocab_size, nhidden=emb_dim).to(self.device)       # pretrain_damsm.py:67
-        self.heads = RegionHeads(out_dim=emb_dim).to(self.device)                            # :68 (trainable part)
+        self.heads = RegionHeads(out_dim=emb_dim, native=native_head).to(self.device)        # :68 (trainable part)
         params = list(self.rnn.parameters()) + [p for p in self.heads.parameters() if p.requires_grad]
         # capturable: the step counter lives on the device, so the optimiser step can sit inside a CUDA graph
         self.optimizer = torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), capturable=True)   # :74

@@ -23,6 +23,7 @@ from .agb_native import native, ops  # noqa: E402,F401
 from .agb_native.graph import GraphedStep  # noqa: E402,F401
 from .agb_native.pipeline import HostPrefetcher  # noqa: E402,F401
 from .networks.attention import AttentionModule, GlobalAttention, func_attention  # noqa: E402,F401
+from .networks.region_head import RegionFeatureHead  # noqa: E402,F401
 from .losses.words_loss import WordsLoss  # noqa: E402,F401
 from .losses.sentence_loss import SentenceLoss  # noqa: E402,F401
 from .losses.damsm_loss import DAMSMLoss  # noqa: E402,F401

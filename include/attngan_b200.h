@@ -213,6 +213,23 @@ int agb_contrastive_fwd(const float* raw, int B, const int32_t* class_ids, const
                         float* draw, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Region-feature head of the image encoder
+ * replaces CNNEncoder.emb_features = conv1x1(Cin=768 -> Cout=256, no bias) on the Mixed_6e map and its autograd
+ *          networks/cnn_encoder.py:56,101; utilities/layers.py:46-48
+ *   x     [B,Cin,R]   fp32 contiguous (R = 17*17)         w  [Cout,Cin] fp32 (emb_features.weight [Cout,Cin,1,1])
+ *   feat  [B,Cout,R]  fp32 out: what the reference hands to WordsLoss as img_features
+ *   dfeat [B,Cout,R]  fp32;  dw [Cout,Cin] fp32 out or NULL;  dx [B,Cin,R] fp32 out or NULL (frozen trunk)
+ * Both run on tcgen05 (16-bit operands cast once into the workspace, fp32 accumulation in TMEM): the forward in split
+ * precision (hi + lo fp16 pairs: fp32-accurate features), the backward in bf16.  Limits: Cin % 64 == 0,
+ * Cout % 128 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+size_t agb_region_head_workspace_bytes(int B, int Cin, int Cout, int R);
+int agb_region_head_fwd(const float* x, const float* w, float* feat, void* workspace, size_t workspace_bytes,
+                        int B, int Cin, int Cout, int R, void* stream);
+int agb_region_head_bwd(const float* x, const float* w, const float* dfeat, float* dw, float* dx, void* workspace,
+                        size_t workspace_bytes, int B, int Cin, int Cout, int R, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Functional region-word attention on its own
  * replaces func_attention(query, context, gamma1, scaled)    networks/attention.py:82-121
  *   query [B,D,L] fp32 strided, context [B,D,R] fp32 contiguous

@@ -57,7 +57,7 @@ SIGNATURES = {
     "agb_region_head_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
                                     c_void_p]),
     "agb_region_head_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
-                                    c_int, c_int, c_int, c_void_p]),
+                                    c_int, c_int, c_int, c_int, c_void_p]),
     "agb_func_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "agb_func_attention_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                        c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t,

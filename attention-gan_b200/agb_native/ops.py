@@ -220,8 +220,9 @@ def func_attention_bwd(query, context, gamma1, scaled, dwc, dattn, need_dquery=T
 # ------------------------------------------------------------------------------------------------
 # region-feature head of the image encoder                reference networks/cnn_encoder.py:56,101
 # ------------------------------------------------------------------------------------------------
-def region_head_fwd(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """x [B,Cin,R] fp32 contiguous, weight [Cout,Cin] fp32 -> feat [B,Cout,R] fp32 (tcgen05, split precision)"""
+def region_head_fwd(x: torch.Tensor, weight: torch.Tensor, keep_ws: bool = False):
+    """x [B,Cin,R] fp32 contiguous, weight [Cout,Cin] fp32 -> feat [B,Cout,R] fp32 (tcgen05, split precision);
+    with keep_ws also the workspace, whose 16-bit operand copies region_head_bwd(ws=...) reuses"""
     require_cuda(x, weight)
     B, Cin, R = x.shape
     Cout = weight.shape[0]
@@ -232,20 +233,23 @@ def region_head_fwd(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     feat = torch.empty((B, Cout, R), dtype=torch.float32, device=x.device)
     rc = N.lib().agb_region_head_fwd(_p(x), _p(weight), _p(feat), _p(ws), ws.numel(), B, Cin, Cout, R, _stream(x))
     N.check(rc, "agb_region_head_fwd")
-    return feat
+    return (feat, ws) if keep_ws else feat
 
 
-def region_head_bwd(x: torch.Tensor, weight: torch.Tensor, dfeat: torch.Tensor, need_dw: bool, need_dx: bool):
-    """Returns (dweight [Cout,Cin] or None, dx [B,Cin,R] or None)"""
+def region_head_bwd(x: torch.Tensor, weight: torch.Tensor, dfeat: torch.Tensor, need_dw: bool, need_dx: bool,
+                    ws: Optional[torch.Tensor] = None):
+    """Returns (dweight [Cout,Cin] or None, dx [B,Cin,R] or None); ws: the workspace of the matching forward"""
     require_cuda(x, weight, dfeat)
     B, Cin, R = x.shape
     Cout = weight.shape[0]
-    ws = _ws(N.lib().agb_region_head_workspace_bytes(B, Cin, Cout, R), x.device)
+    from_fwd = 1 if ws is not None else 0
+    if ws is None:
+        ws = _ws(N.lib().agb_region_head_workspace_bytes(B, Cin, Cout, R), x.device)
     dw = torch.empty((Cout, Cin), dtype=torch.float32, device=x.device) if need_dw else None
     dx = torch.empty_like(x) if need_dx else None
     if not (need_dw or need_dx):
         return None, None
-    rc = N.lib().agb_region_head_bwd(_p(x), _p(weight), _p(dfeat), _p(dw), _p(dx), _p(ws), ws.numel(), B, Cin, Cout, R,
-                                     _stream(x))
+    rc = N.lib().agb_region_head_bwd(_p(x), _p(weight), _p(dfeat), _p(dw), _p(dx), _p(ws), ws.numel(), from_fwd,
+                                     B, Cin, Cout, R, _stream(x))
     N.check(rc, "agb_region_head_bwd")
     return dw, dx

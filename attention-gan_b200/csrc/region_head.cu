@@ -8,13 +8,16 @@
 //                                                                             DAMSM pretraining, pretrain_damsm.py:70-74)
 //             dx[b][c, r]   = sum_o W[o, c] dfeat[b][o, r]                   (optional: the Inception trunk is frozen)
 //
-// PyTorch runs this convolution in fp32 on CUDA cores (TF32 is off by default): 29 GFLOP forward at batch 256.
+// PyTorch runs this convolution through cuDNN, by default with TF32 operands (10 mantissa bits; exact fp32 only with
+// torch.backends.cudnn.allow_tf32 = False, then on CUDA cores): 29 GFLOP per direction at batch 256.
 // Here the operands are cast once to 16 bit (rows padded from R = 289 to 320 columns: a 578-byte row pitch is not
 // TMA-addressable) and the GEMMs run on the batched tcgen05 kernel of tc_gemm.cu:
-//   * forward in SPLIT precision: x = x_hi + x_lo, W = W_hi + W_lo (fp16 pairs); W_hi x_hi + W_lo x_hi (one launch,
-//     two operand pairs) + W_hi x_lo (accumulating launch): fp32-accurate features, because they feed the loss that
-//     is held to 1e-4;
-//   * backward in bf16 (range of the gradients, which can be ~1e-8; their precision needs are those of a gradient).
+//   * forward in SPLIT precision: x = x_hi + x_lo, W = W_hi + W_lo (bf16 pairs, 16 significant bits); W_hi x_hi +
+//     W_lo x_hi (one launch, two operand pairs) + W_hi x_lo (accumulating launch): features within ~1e-5 of fp32
+//     arithmetic (PyTorch's default for this convolution on the GPU is TF32: 5e-4), because they feed the loss that is
+//     held to 1e-4;
+//   * backward with plain bf16 operands (the gradients can be ~1e-8: bf16 has fp32's range; their precision needs
+//     are those of a gradient), reusing x_hi / W_hi of the forward call when the caller hands the workspace back.
 // The features leave as fp32 [B, Cout, R] (the layout the reference hands to WordsLoss); packing them into the 16-bit
 // operand layouts of the pair kernels stays in pack_img_kernel_tc (0.4 % of the step at batch 2048).
 #include <algorithm>
@@ -25,21 +28,23 @@ namespace agb {
 namespace {
 
 constexpr int kPad = 64;
+constexpr int kRowsPerBlock = 8;
+static unsigned cast_grid(size_t rows) { return (unsigned)((rows + kRowsPerBlock - 1) / kRowsPerBlock); }
 
 // src fp32 [rows, R] -> hi (and lo) 16-bit [rows, Rp], columns >= R zero
 template <typename T16>
 __global__ void cast_pad_kernel(const float* __restrict__ src, T16* __restrict__ hi, T16* __restrict__ lo, int R,
                                 int Rp, size_t rows) {
-  const size_t row = blockIdx.x;
-  if (row >= rows) return;
-  const float* s = src + row * R;
-  T16* h = hi + row * Rp;
-  T16* l = lo ? lo + row * Rp : nullptr;
-  for (int r = threadIdx.x; r < Rp; r += blockDim.x) {
-    const float v = r < R ? s[r] : 0.f;
+  // kRowsPerBlock consecutive rows per CTA: the source rows are contiguous, so the block streams one span
+  const size_t row0 = (size_t)blockIdx.x * kRowsPerBlock;
+  const int nrow = (int)min((size_t)kRowsPerBlock, rows > row0 ? rows - row0 : 0);
+  for (int i = threadIdx.x; i < nrow * Rp; i += blockDim.x) {
+    const int k = i / Rp, r = i - k * Rp;
+    const size_t row = row0 + k;
+    const float v = r < R ? src[row * R + r] : 0.f;
     const T16 a = from_f32<T16>(v);
-    h[r] = a;
-    if (l) l[r] = from_f32<T16>(v - to_f32(a));
+    hi[row * Rp + r] = a;
+    if (lo) lo[row * Rp + r] = from_f32<T16>(v - to_f32(a));
   }
 }
 
@@ -54,7 +59,7 @@ __global__ void sum_slices_kernel(const float* __restrict__ part, int slices, si
 
 struct HeadPlan {
   int Rp, splits;
-  size_t off_xh, off_xl, off_wh, off_wl, off_xb, off_wb, off_db, off_part, total;
+  size_t off_xh, off_xl, off_wh, off_wl, off_db, off_part, total;
 };
 HeadPlan make_plan(int B, int Cin, int Cout, int R) {
   HeadPlan p;
@@ -67,8 +72,6 @@ HeadPlan make_plan(int B, int Cin, int Cout, int R) {
   p.off_xl = take(x16);
   p.off_wh = take(w16);
   p.off_wl = take(w16);
-  p.off_xb = take(x16);                                       // bf16 copy of x for the backward
-  p.off_wb = take(w16);
   p.off_db = take((size_t)B * Cout * p.Rp * 2);               // bf16 d feat
   p.off_part = take((size_t)p.splits * Cout * Cin * 4);
   p.total = o;
@@ -103,23 +106,23 @@ extern "C" int agb_region_head_fwd(const float* x, const float* w, float* feat, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  __half* xh = (__half*)(ws + pl.off_xh);
-  __half* xl = (__half*)(ws + pl.off_xl);
-  __half* wh = (__half*)(ws + pl.off_wh);
-  __half* wl = (__half*)(ws + pl.off_wl);
-  cast_pad_kernel<__half><<<(unsigned)((size_t)B * Cin), 128, 0, st>>>(x, xh, xl, R, pl.Rp, (size_t)B * Cin);
+  __nv_bfloat16* xh = (__nv_bfloat16*)(ws + pl.off_xh);
+  __nv_bfloat16* xl = (__nv_bfloat16*)(ws + pl.off_xl);
+  __nv_bfloat16* wh = (__nv_bfloat16*)(ws + pl.off_wh);
+  __nv_bfloat16* wl = (__nv_bfloat16*)(ws + pl.off_wl);
+  cast_pad_kernel<__nv_bfloat16><<<cast_grid((size_t)B * Cin), 256, 0, st>>>(x, xh, xl, R, pl.Rp, (size_t)B * Cin);
   if (int rc = check_launch("cast_pad_kernel")) return rc;
-  cast_pad_kernel<__half><<<Cout, 256, 0, st>>>(w, wh, wl, Cin, Cin, (size_t)Cout);
+  cast_pad_kernel<__nv_bfloat16><<<cast_grid(Cout), 256, 0, st>>>(w, wh, wl, Cin, Cin, (size_t)Cout);
   if (int rc = check_launch("cast_pad_kernel")) return rc;
 
   CUtensorMap mWh, mWl, mXh, mXl;
-  if (int rc = tc::make_tmap_2d(&mWh, wh, Cout, Cin, 128, false)) return rc;
-  if (int rc = tc::make_tmap_2d(&mWl, wl, Cout, Cin, 128, false)) return rc;
-  if (int rc = tc::make_tmap_2d(&mXh, xh, (uint64_t)B * Cin, pl.Rp, 64, false)) return rc;
-  if (int rc = tc::make_tmap_2d(&mXl, xl, (uint64_t)B * Cin, pl.Rp, 64, false)) return rc;
+  if (int rc = tc::make_tmap_2d(&mWh, wh, Cout, Cin, 128, true)) return rc;
+  if (int rc = tc::make_tmap_2d(&mWl, wl, Cout, Cin, 128, true)) return rc;
+  if (int rc = tc::make_tmap_2d(&mXh, xh, (uint64_t)B * Cin, pl.Rp, 64, true)) return rc;
+  if (int rc = tc::make_tmap_2d(&mXl, xl, (uint64_t)B * Cin, pl.Rp, 64, true)) return rc;
   // feat[z][o, r] = sum_c W[o, c] x[z][c, r]:  A = W K-major (rows o, cols c), B = x[z] MN-major (rows c, cols r)
   tc::TcGemmArgs g{};
-  g.a_mn = 0; g.b_mn = 1; g.bf16 = 0; g.M = Cout; g.N = R; g.K = Cin; g.KB = 1;
+  g.a_mn = 0; g.b_mn = 1; g.bf16 = 1; g.M = Cout; g.N = R; g.K = Cin; g.KB = 1;
   g.NT = 128; g.NT0 = (pl.Rp == 320 && R > 192) ? 192 : 0; g.MT = 2;
   g.b_zrow = Cin; g.b2_zrow = Cin;
   g.C = feat; g.c_z = (int64_t)Cout * R; g.c_m = R; g.c_n = 1; g.alpha = 1.f;
@@ -130,8 +133,8 @@ extern "C" int agb_region_head_fwd(const float* x, const float* w, float* feat, 
 }
 
 extern "C" int agb_region_head_bwd(const float* x, const float* w, const float* dfeat, float* dw, float* dx,
-                                   void* workspace, size_t workspace_bytes, int B, int Cin, int Cout, int R,
-                                   void* stream) {
+                                   void* workspace, size_t workspace_bytes, int ws_from_fwd, int B, int Cin, int Cout,
+                                   int R, void* stream) {
   if (int rc = check(B, Cin, Cout, R)) return rc;
   if (!x || !w || !dfeat || !workspace || (!dw && !dx)) return fail_arg("null pointer");
   const HeadPlan pl = make_plan(B, Cin, Cout, R);
@@ -141,16 +144,18 @@ extern "C" int agb_region_head_bwd(const float* x, const float* w, const float* 
   }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  __nv_bfloat16* xb = (__nv_bfloat16*)(ws + pl.off_xb);
-  __nv_bfloat16* wb = (__nv_bfloat16*)(ws + pl.off_wb);
+  __nv_bfloat16* xb = (__nv_bfloat16*)(ws + pl.off_xh);       // the hi parts double as the plain bf16 operands
+  __nv_bfloat16* wb = (__nv_bfloat16*)(ws + pl.off_wh);
   __nv_bfloat16* db = (__nv_bfloat16*)(ws + pl.off_db);
   float* part = (float*)(ws + pl.off_part);
-  cast_pad_kernel<__nv_bfloat16><<<(unsigned)((size_t)B * Cout), 128, 0, st>>>(dfeat, db, nullptr, R, pl.Rp, (size_t)B * Cout);
+  cast_pad_kernel<__nv_bfloat16><<<cast_grid((size_t)B * Cout), 256, 0, st>>>(dfeat, db, nullptr, R, pl.Rp, (size_t)B * Cout);
   if (int rc = check_launch("cast_pad_kernel")) return rc;
   CUtensorMap mD_k, mD_mn, mX_k, mW_mn;
   if (dw) {
-    cast_pad_kernel<__nv_bfloat16><<<(unsigned)((size_t)B * Cin), 128, 0, st>>>(x, xb, nullptr, R, pl.Rp, (size_t)B * Cin);
-    if (int rc = check_launch("cast_pad_kernel")) return rc;
+    if (!ws_from_fwd) {
+      cast_pad_kernel<__nv_bfloat16><<<cast_grid((size_t)B * Cin), 256, 0, st>>>(x, xb, nullptr, R, pl.Rp, (size_t)B * Cin);
+      if (int rc = check_launch("cast_pad_kernel")) return rc;
+    }
     // dW[o, c] = sum_b sum_r dfeat[b][o, r] x[b][c, r]: both operands K-major over the (zero-padded) regions,
     // the images are the reduction blocks, cut into `splits` slices whose partial sums are added in a fixed order
     if (int rc = tc::make_tmap_2d(&mD_k, db, (uint64_t)B * Cout, pl.Rp, 128, true)) return rc;
@@ -167,8 +172,10 @@ extern "C" int agb_region_head_bwd(const float* x, const float* w, const float* 
     if (int rc = check_launch("sum_slices_kernel")) return rc;
   }
   if (dx) {
-    cast_pad_kernel<__nv_bfloat16><<<Cout, 256, 0, st>>>(w, wb, nullptr, Cin, Cin, (size_t)Cout);
-    if (int rc = check_launch("cast_pad_kernel")) return rc;
+    if (!ws_from_fwd) {
+      cast_pad_kernel<__nv_bfloat16><<<cast_grid(Cout), 256, 0, st>>>(w, wb, nullptr, Cin, Cin, (size_t)Cout);
+      if (int rc = check_launch("cast_pad_kernel")) return rc;
+    }
     // dx[z][c, r] = sum_o W[o, c] dfeat[z][o, r]: A = W MN-major (rows o = k, cols c = m), B = dfeat[z] MN-major
     if (int rc = tc::make_tmap_2d(&mW_mn, wb, Cout, Cin, 64, true)) return rc;
     if (int rc = tc::make_tmap_2d(&mD_mn, db, (uint64_t)B * Cout, pl.Rp, 64, true)) return rc;

@@ -3,8 +3,9 @@
 ``RegionFeatureHead(out_dim)`` is the ``emb_features`` 1x1 convolution of the reference's ``CNNEncoder``
 (networks/cnn_encoder.py:56,101: ``Layers.conv1x1(768, out_dim)``, no bias) with the same parameter name and
 shape (``emb_features.weight [out_dim, 768, 1, 1]``), so the head entries of ``CNNEncoder.pkl`` load unchanged.
-Forward and backward run on tcgen05 through the C ABI (``agb_region_head_fwd/bwd``): PyTorch computes this
-convolution in fp32 on CUDA cores (TF32 is off by default), 29 GFLOP per direction at batch 256.
+Forward and backward run on tcgen05 through the C ABI (``agb_region_head_fwd/bwd``): the forward with split
+bf16 operands (features within ~1e-5 of fp32 arithmetic; cuDNN's default for this convolution is TF32, 5e-4),
+the backward with plain bf16 operands.
 """
 from __future__ import annotations
 
@@ -21,8 +22,9 @@ class _RegionHead(torch.autograd.Function):
         x3 = (x if x.dtype == torch.float32 else x.float()).reshape(B, Cin, H * W).contiguous()
         w2 = weight.reshape(weight.shape[0], Cin)
         w2 = (w2 if w2.dtype == torch.float32 else w2.float()).contiguous()
-        feat = ops.region_head_fwd(x3.detach(), w2.detach())
+        feat, ws = ops.region_head_fwd(x3.detach(), w2.detach(), keep_ws=True)
         ctx.save_for_backward(x3, w2)
+        ctx.ws = ws if any(ctx.needs_input_grad) else None        # bf16 copies of x and W, reused by backward
         ctx.meta = (x.shape, x.dtype, weight.shape, weight.dtype)
         return feat.reshape(B, weight.shape[0], H, W).to(x.dtype)
 
@@ -31,7 +33,8 @@ class _RegionHead(torch.autograd.Function):
         x3, w2 = ctx.saved_tensors
         xshape, xdt, wshape, wdt = ctx.meta
         d3 = dfeat.float().reshape(x3.shape[0], w2.shape[0], -1).contiguous()
-        dw, dx = ops.region_head_bwd(x3, w2, d3, ctx.needs_input_grad[1], ctx.needs_input_grad[0])
+        dw, dx = ops.region_head_bwd(x3, w2, d3, ctx.needs_input_grad[1], ctx.needs_input_grad[0], ctx.ws)
+        ctx.ws = None
         if dw is not None:
             dw = dw.reshape(wshape).to(wdt)
         if dx is not None:

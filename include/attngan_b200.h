@@ -219,15 +219,17 @@ int agb_contrastive_fwd(const float* raw, int B, const int32_t* class_ids, const
  *   x     [B,Cin,R]   fp32 contiguous (R = 17*17)         w  [Cout,Cin] fp32 (emb_features.weight [Cout,Cin,1,1])
  *   feat  [B,Cout,R]  fp32 out: what the reference hands to WordsLoss as img_features
  *   dfeat [B,Cout,R]  fp32;  dw [Cout,Cin] fp32 out or NULL;  dx [B,Cin,R] fp32 out or NULL (frozen trunk)
- * Both run on tcgen05 (16-bit operands cast once into the workspace, fp32 accumulation in TMEM): the forward in split
- * precision (hi + lo fp16 pairs: fp32-accurate features), the backward in bf16.  Limits: Cin % 64 == 0,
- * Cout % 128 == 0.
+ *   ws_from_fwd != 0: `workspace` is the untouched buffer of the matching agb_region_head_fwd call (same x, w):
+ *                     its 16-bit copies of x and w are reused
+ * Both run on tcgen05 (bf16 operands cast once into the workspace, fp32 accumulation in TMEM): the forward in split
+ * precision (hi + lo bf16 pairs: features within ~1e-5 of fp32 arithmetic), the backward with plain bf16 operands.
+ * Limits: Cin % 64 == 0, Cout % 128 == 0.
  * ---------------------------------------------------------------------------------------------- */
 size_t agb_region_head_workspace_bytes(int B, int Cin, int Cout, int R);
 int agb_region_head_fwd(const float* x, const float* w, float* feat, void* workspace, size_t workspace_bytes,
                         int B, int Cin, int Cout, int R, void* stream);
 int agb_region_head_bwd(const float* x, const float* w, const float* dfeat, float* dw, float* dx, void* workspace,
-                        size_t workspace_bytes, int B, int Cin, int Cout, int R, void* stream);
+                        size_t workspace_bytes, int ws_from_fwd, int B, int Cin, int Cout, int R, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Functional region-word attention on its own

@@ -15,7 +15,8 @@
 // Operands reach the tensor core by TMA (128B swizzle, K-major); accumulators live in TMEM:
 // columns [0,256) = two S buffers (MMA of M-tile j+1 overlaps epilogue 1 of M-tile j),
 // columns [256,512) = V.  Warp roles: 0..11 = three epilogue warpgroups, 12 = TMA producer and
-// TMEM allocator, 13 = MMA issuer (448 threads: 144 registers per thread for the epilogues).
+// TMEM allocator, 13 = MMA issuer (448 threads = 14 warps; with 4 warps on an SM sub-partition its 16K registers cap
+// every thread at 128).
 //
 // HBM layout of the pre-packed operands (written by the pack kernels below, 16-bit):
 //   Wh [tiles*128, 256]   packed caption words, K-major rows; unused rows are zero

@@ -15,7 +15,8 @@
 //   epilogue 2 thread = pixel: ctx -> global (lanes = consecutive pixels: coalesced)
 //
 // TMEM: 2 tile buffers x (NT score/P columns + C context columns) = 128 columns per CTA at
-// T <= 32, C <= 32 (256 otherwise), so up to 4 CTAs share an SM and each keeps two tiles in flight.  Warps: 0 = TMA, 1 = MMA, 2-5 = epilogue.
+// T <= 32, C <= 32 (256 otherwise), so several CTAs share an SM and each keeps two tiles in flight.  The warp
+// roles are listed at each kernel (forward: 10 warps; backward: 14 warps).
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>

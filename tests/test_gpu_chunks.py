@@ -39,6 +39,18 @@ def _rel(x, ref):
     return np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30)
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle_bwd(key, img, wrd, lens, dm):
+    """fp64 closed-form gradients, computed once per input set (the parametrised cases share their inputs)"""
+    if key not in _ORACLE_CACHE:
+        B = img.shape[0]
+        _ORACLE_CACHE[key] = cf.words_similarity_bwd(img.numpy().reshape(B, 256, -1), wrd.numpy(), lens.numpy(),
+                                                     dm.cpu().numpy())
+    return _ORACLE_CACHE[key]
+
+
 def _fwd_bwd(ops, native, img3, wrd, l32, dm, math, need_dwords=True):
     m, _, _, ws = ops.damsm_fwd(img3, wrd, l32, 4.0, 5.0, 1e-8, 0, False, math, keep_ws=True,
                                 save=math != native.AGB_MATH_FP32)
@@ -81,7 +93,7 @@ def test_multi_chunk_backward_matches_single_chunk_fp32_and_oracle(agb, chunk_bu
     _, dimg32, dw32 = _fwd_bwd(ops, native, img3, wd, l32, dm, native.AGB_MATH_FP32)
     gtol = 5e-3 if math == "f16" else 2e-2
     assert _rel(dimg2, dimg32) < gtol and _rel(dw2, dw32) < gtol
-    dc0, dw0 = cf.words_similarity_bwd(img.numpy().reshape(B, 256, -1), wrd.numpy(), lens.numpy(), dm.cpu().numpy())
+    dc0, dw0 = _oracle_bwd("b64-seed640", img, wrd, lens, dm)
     assert _rel(dimg2, dc0) < gtol
     assert _rel(dw2.transpose(1, 2), dw0) < gtol
     assert _rel(dimg32, dc0) < 1e-4 and _rel(dw32.transpose(1, 2), dw0) < 1e-4

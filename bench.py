@@ -606,7 +606,10 @@ def damsm_roofline(m, peaks, long_step):
                            "d img 2, d words 1 = 12*R*L*D per pair (recomputation is not counted)",
             "step": {"achieved": step_tf, "frac": step_tf / peak, "frac_of_burst": step_tf / peaks["tf_burst"],
                      "note": "all 12*R*L*D flop per pair of this rank / device-timed step"},
-            "kernels": kernels}
+            "kernels": kernels,
+            "concurrency_note": "the d img and d words GEMMs run concurrently on two streams: their event durations "
+                                "overlap in time and are NOT additive (serialised under ncu the d words GEMM is ~4x "
+                                "shorter, profiles/r2_launches_cfg4_n1.csv); the pair kernels run alone"}
     return roof
 
 

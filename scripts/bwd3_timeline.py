@@ -1,3 +1,5 @@
+"""NOTE (round 2): the clock64 timeline is compiled out of release builds; rebuild the library with -DAGB_TIMELINE
+(add it to FLAGS in attention-gan_b200/agb_native/build_native.py) before running this script."""
 """Timeline of CTA 0 of damsm_bwd3_kernel (AGB_DAMSM_DEBUG=16): when the MMA issuer, the TMA producer and three
 epilogue warps reach each region tile.  Times in microseconds from the first stamp (SM clock at 1.965 GHz)."""
 import ctypes, os, sys

@@ -388,10 +388,11 @@ def test_native_rejects_unsupported_shapes(agb):
         mod(torch.zeros(1, 8, 2, 2, device="cuda"), torch.zeros(1, 16, 65, device="cuda"))
 
 
-@pytest.mark.parametrize("math", ["fp32", "f16"])
-def test_nccl_sharded_losses_equal_single_process(math):
-    """2 ranks over NCCL: loss and all gradients equal the single-process result on the
-    concatenated batch (needs >= 2 GPUs; the CPU suite covers the same logic over gloo)."""
+@pytest.mark.parametrize("math,ragged", [("fp32", False), ("f16", False), ("f16x2", True), ("f16", True)])
+def test_nccl_sharded_losses_equal_single_process(math, ragged):
+    """2 ranks over NCCL: loss and all gradients equal the single-process result on the concatenated batch AND the
+    fp64 oracle; `ragged`: the second rank's captions are padded to T - 1 only
+    (needs >= 2 GPUs; the CPU suite covers the same logic over gloo)."""
     import os
     import subprocess
     import sys
@@ -399,7 +400,8 @@ def test_nccl_sharded_losses_equal_single_process(math):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "check_sharded.py"), "64", math]
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "check_sharded.py"), "64", math] + \
+        (["ragged"] if ragged else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout

@@ -248,3 +248,29 @@ def test_sharded_losses_with_different_caption_padding_per_rank():
         T_r = 4 if r == 1 else 5
         assert o["dwords"].shape[2] == T_r
         np.testing.assert_allclose(o["dwords"], dw0[sl][:, :, :T_r], rtol=1e-4, atol=1e-6)
+
+
+def test_options_and_helpers_without_a_gpu():
+    """agb_set_option validates names on the host; the graph / prefetch helpers refuse to run without CUDA"""
+    import attention_gan_b200 as pkg
+    lib = pkg.native.lib()
+    assert lib.agb_set_option(b"damsm_chunk_mb", 16384) == 0
+    assert lib.agb_set_option(b"no_such_option", 1) == -1 and b"unknown option" in lib.agb_last_error()
+    with pytest.raises(pkg.native.NativeError):
+        pkg.native.set_option("no_such_option", 1)
+    # workspace sizes follow the staging budget (the tests force the multi-chunk path this way)
+    big = lib.agb_damsm_workspace_bytes(64, 64, 18, 256, 289, pkg.native.AGB_MATH_TC_F16)
+    pkg.native.set_option("damsm_chunk_mb", 11)
+    small = lib.agb_damsm_workspace_bytes(64, 64, 18, 256, 289, pkg.native.AGB_MATH_TC_F16)
+    pkg.native.set_option("damsm_chunk_mb", 16384)
+    assert 0 < small < big
+    # split precision needs the lo operand copies
+    assert lib.agb_damsm_workspace_bytes(64, 64, 18, 256, 289, pkg.native.AGB_MATH_TC_F16X2) > big
+    assert lib.agb_damsm_supported(18, 256, 289, pkg.native.AGB_MATH_TC_F16X2) == 1
+    assert lib.agb_region_head_workspace_bytes(4, 768, 256, 289) > 0
+    assert lib.agb_region_head_workspace_bytes(4, 100, 96, 289) == 0
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            pkg.GraphedStep(lambda: None)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            pkg.HostPrefetcher("cuda")

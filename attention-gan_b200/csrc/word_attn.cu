@@ -447,15 +447,18 @@ __device__ __forceinline__ void stage_words(float* x_s, const float* __restrict_
 __global__ void __launch_bounds__(1024)
 project_words_kernel(const float* __restrict__ conv_w, const float* __restrict__ words, int64_t ws_b, int64_t ws_e,
                      int64_t ws_t, float* __restrict__ we, int C, int E, int T) {
+  // gridDim.y CTAs per sample, each with a slice of the channels (the per-sample work is latency-bound: smaller
+  // slices on more SMs finish sooner, and the weight slice is all a CTA has to stage)
   extern __shared__ float sm_[];
-  float* w_s = sm_;                               // [C][E + 1]
-  float* x_s = sm_ + (size_t)C * (E + 1);         // [T][E + 1]
   const int b = blockIdx.x, P = E + 1;
+  const int cs = (C + gridDim.y - 1) / gridDim.y, c0 = blockIdx.y * cs, nc = max(0, min(cs, C - c0));
+  float* w_s = sm_;                               // [nc][E + 1]
+  float* x_s = sm_ + (size_t)cs * (E + 1);        // [T][E + 1]
 #pragma unroll 8
-  for (int i = threadIdx.x; i < C * E; i += blockDim.x) w_s[(i / E) * P + (i % E)] = conv_w[i];
+  for (int i = threadIdx.x; i < nc * E; i += blockDim.x) w_s[(i / E) * P + (i % E)] = conv_w[(size_t)c0 * E + i];
   stage_words(x_s, words, ws_b, ws_e, ws_t, b, E, T);
   __syncthreads();
-  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+  for (int i = threadIdx.x; i < nc * T; i += blockDim.x) {
     const int c = i / T, t = i - c * T;
     const float* w = w_s + c * P;
     const float* x = x_s + t * P;
@@ -468,7 +471,7 @@ project_words_kernel(const float* __restrict__ conv_w, const float* __restrict__
       a3 = fmaf(w[e + 3], x[e + 3], a3);
     }
     for (; e < E; ++e) a0 = fmaf(w[e], x[e], a0);
-    we[(size_t)b * C * T + i] = (a0 + a1) + (a2 + a3);
+    we[(size_t)b * C * T + (size_t)c0 * T + i] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -482,11 +485,14 @@ project_words_bwd_kernel(const float* __restrict__ part, int slots, int tiles, i
                          const float* __restrict__ conv_w, const float* __restrict__ words, int64_t ws_b,
                          int64_t ws_e, int64_t ws_t, float* __restrict__ dwe, float* __restrict__ dwords,
                          float* __restrict__ dwp, int C, int E, int T) {
+  // gridDim.y CTAs per sample, each with a slice [e0, e0 + ne) of the embedding index (both outputs are
+  // independent per e); every slice re-forms the small dwe[b] (C*T values), slice 0 stores it
   extern __shared__ float sm_[];
-  const int b = blockIdx.x, P = E + 1;
+  const int b = blockIdx.x;
+  const int es = (E + gridDim.y - 1) / gridDim.y, e0 = blockIdx.y * es, ne = max(0, min(es, E - e0)), P = es + 1;
   float* d_s = sm_;                               // [C][T]
-  float* w_s = d_s + C * T;                       // [C][E + 1]
-  float* x_s = w_s + (size_t)C * P;               // [T][E + 1]
+  float* w_s = d_s + C * T;                       // [C][es + 1]
+  float* x_s = w_s + (size_t)C * P;               // [T][es + 1]
   int n = slots;
   if (G > 0) {
     const long long first = (((long long)b * tiles + 1) * G + total - 1) / total - 1;
@@ -499,28 +505,35 @@ project_words_bwd_kernel(const float* __restrict__ part, int slots, int tiles, i
 #pragma unroll 4
     for (int k = 0; k < n; ++k) acc += p[(size_t)k * C * T];
     d_s[i] = acc;
-    dwe[(size_t)b * C * T + i] = acc;
+    if (blockIdx.y == 0) dwe[(size_t)b * C * T + i] = acc;
   }
   if (dwords != nullptr) {
 #pragma unroll 8
-    for (int i = threadIdx.x; i < C * E; i += blockDim.x) w_s[(i / E) * P + (i % E)] = conv_w[i];
+    for (int i = threadIdx.x; i < C * ne; i += blockDim.x) w_s[(i / ne) * P + (i % ne)] = conv_w[(size_t)(i / ne) * E + e0 + (i % ne)];
   }
-  if (dwp != nullptr) stage_words(x_s, words, ws_b, ws_e, ws_t, b, E, T);
+  if (dwp != nullptr) {
+#pragma unroll 8
+    for (int i = threadIdx.x; i < ne * T; i += blockDim.x) {
+      // walk the source along its contiguous dimension
+      const int e = ws_e == 1 ? i % ne : i / T, t = ws_e == 1 ? i / ne : i % T;
+      x_s[t * P + e] = words[(int64_t)b * ws_b + (int64_t)(e0 + e) * ws_e + (int64_t)t * ws_t];
+    }
+  }
   __syncthreads();
   if (dwords != nullptr) {
-    for (int i = threadIdx.x; i < E * T; i += blockDim.x) {      // lanes = consecutive e: conflict-free
-      const int t = i / E, e = i - t * E;
+    for (int i = threadIdx.x; i < ne * T; i += blockDim.x) {      // lanes = consecutive e: conflict-free
+      const int t = i / ne, e = i - t * ne;
       float acc = 0.f;
       for (int c = 0; c < C; ++c) acc = fmaf(w_s[c * P + e], d_s[c * T + t], acc);
-      dwords[((size_t)b * E + e) * T + t] = acc;
+      dwords[((size_t)b * E + e0 + e) * T + t] = acc;
     }
   }
   if (dwp != nullptr) {
-    for (int i = threadIdx.x; i < C * E; i += blockDim.x) {
-      const int c = i / E, e = i - c * E;
+    for (int i = threadIdx.x; i < C * ne; i += blockDim.x) {
+      const int c = i / ne, e = i - c * ne;
       float acc = 0.f;
       for (int t = 0; t < T; ++t) acc = fmaf(d_s[c * T + t], x_s[t * P + e], acc);
-      dwp[((size_t)b * C + c) * E + e] = acc;
+      dwp[((size_t)b * C + c) * E + e0 + e] = acc;
     }
   }
 }
@@ -614,12 +627,15 @@ extern "C" int agb_word_attn_fwd(const void* images, const float* words, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   // we[b][c,t] = sum_e W[c,e] words[b][e,t]                     (attention.py:50-52, conv1 1x1)
   {
-    const size_t smem = (size_t)(C + T) * (E + 1) * sizeof(float);
+    // up to 4 channel slices per sample while the batch alone does not fill the GPU
+    const int slices = std::max(1, std::min(std::min(4, C), (2 * device_sms() + B - 1) / B));
+    const int cs = (C + slices - 1) / slices;
+    const size_t smem = (size_t)(cs + T) * (E + 1) * sizeof(float);
     if (smem > 200 * 1024) return fail_unsupported("E=%d is outside the compiled range of the projection kernel", E);
     if (smem > 48 * 1024)
       AGB_CUDA(cudaFuncSetAttribute(project_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = std::min(1024, (C * T + 31) / 32 * 32);
-    project_words_kernel<<<B, threads, smem, st>>>(conv_w, words, ws_b, ws_e, ws_t, we, C, E, T);
+    const int threads = std::min(1024, (cs * T + 31) / 32 * 32);
+    project_words_kernel<<<dim3(B, slices), threads, smem, st>>>(conv_w, words, ws_b, ws_e, ws_t, we, C, E, T);
     if (int rc = check_launch("project_words_kernel")) return rc;
   }
   const float qscale = (scaled ? 1.f / sqrtf((float)C) : 1.f) * kLog2e;
@@ -692,11 +708,13 @@ extern "C" int agb_word_attn_bwd(const void* images, const float* words, int64_t
   // one CTA per sample: dwe[b] = sum of the partial slots; dwords[b][e,t] = sum_c W[c,e] dwe[b][c,t];
   // dwp[b][c,e] = sum_t dwe[b][c,t] words[b][e,t]; then dW[c,e] = sum_b dwp[b][c,e] in a fixed order
   float* dwp = dwe + (size_t)B * C * T;
-  const size_t psmem = ((size_t)C * T + (size_t)(C + T) * (E + 1)) * sizeof(float);
+  const int pslices = std::max(1, std::min(std::min(4, E / 32), (2 * device_sms() + B - 1) / B));   // slices of the embedding index
+  const int pes = (E + pslices - 1) / pslices;
+  const size_t psmem = ((size_t)C * T + (size_t)(C + T) * (pes + 1)) * sizeof(float);
   if (psmem > 200 * 1024) return fail_unsupported("E=%d is outside the compiled range of the projection kernel", E);
   if (psmem > 48 * 1024)
     AGB_CUDA(cudaFuncSetAttribute(project_words_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-  project_words_bwd_kernel<<<B, 1024, psmem, st>>>(
+  project_words_bwd_kernel<<<dim3(B, pslices), pes >= 128 ? 512 : 256, psmem, st>>>(
       part, ntiles, cdiv(HW, 128), G, (long long)B * cdiv(HW, 128), conv_w, words, ws_b, ws_e, ws_t, dwe, dwords,
       dconv_w ? dwp : nullptr, C, E, T);
   if ((rc = check_launch("project_words_bwd_kernel"))) return rc;

@@ -151,12 +151,19 @@ class _WordsLossFn(torch.autograd.Function):
             rnn32 = rnn.detach().float().reshape(rnn.shape[-2], -1).contiguous()
             if ex.W > 1:
                 rnn32 = _gather_cat(rnn32, cfg.group)
-        save = cfg.math != native.AGB_MATH_FP32 and any(ctx.needs_input_grad[:2])   # training forward
+        # the math mode was resolved from the LOCAL caption padding; after the exchange every rank sees the agreed T:
+        # if that leaves the tensor-core range, all ranks fall back to the fp32 kernels together
+        math = cfg.math
+        if math != native.AGB_MATH_FP32 and hasattr(o, "damsm_supported") and \
+                not o.damsm_supported(int(w32.shape[2]), D, int(img3.shape[2]), math):
+            math = native.AGB_MATH_FP32
+        ctx.math = math
+        save = math != native.AGB_MATH_FP32 and any(ctx.needs_input_grad[:2])       # training forward
         m, att, scos, ws = o.damsm_fwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, ex.row0, cfg.want_att,
-                                       cfg.math, cnn32 if fuse_sent else None, rnn32 if fuse_sent else None, True,
+                                       math, cnn32 if fuse_sent else None, rnn32 if fuse_sent else None, True,
                                        save)
         # packed 16-bit operands (and, after a training forward, the saved context vectors), reused by backward
-        ctx.ws = ws if cfg.math != native.AGB_MATH_FP32 else None
+        ctx.ws = ws if math != native.AGB_MATH_FP32 else None
         ctx.ws_saved = save
         m_all = _gather_cat(m, cfg.group) if ex.W > 1 else m
         loss, dm = o.contrastive(m_all, ex.cls, ex.labels, cfg.gamma3, cfg.lam, ex.row0, Bl)
@@ -184,7 +191,7 @@ class _WordsLossFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[1]
         gscale = dloss.detach().float().reshape(1).contiguous()
         dimg, dwords = cfg.ops.damsm_bwd(img3, w32, ex.lens, cfg.gamma1, cfg.gamma2, cfg.eps, dm, gscale, need_w,
-                                         cfg.math, m, ctx.ws, ctx.ws_saved)
+                                         ctx.math, m, ctx.ws, ctx.ws_saved)
         ctx.ws = None
         if dwords is not None:
             if ex.W > 1:

@@ -108,7 +108,11 @@ def damsm_fwd(img: torch.Tensor, words: torch.Tensor, cap_lens: torch.Tensor, ga
     Bc, _, T = words.shape
     dev = img.device
     m = torch.empty((Bi, Bc), dtype=torch.float32, device=dev)
-    att = torch.zeros((Bi, T, R), dtype=torch.float32, device=dev) if want_att else None
+    # the fp32 pair kernel writes only the live word rows of the matched-pair maps; the tensor-core path's
+    # diag_att_kernel writes every row (zeros for t >= L), so it needs no zero fill
+    att = None
+    if want_att:
+        att = (torch.zeros if math == N.AGB_MATH_FP32 else torch.empty)((Bi, T, R), dtype=torch.float32, device=dev)
     scos = torch.empty((Bi, Bc), dtype=torch.float32, device=dev) if cnn is not None else None
     nbytes = N.lib().agb_damsm_workspace_bytes(Bi, Bc, T, D, R, math)
     if nbytes == 0:

@@ -396,9 +396,9 @@ static int run_pack(const float* img, const float* words, int64_t ws_b, int64_t 
   int32_t* uncap = pl.split ? (int32_t*)(ws + pl.off_uncap) : nullptr;
   int32_t* nunits = pl.split ? (int32_t*)(ws + pl.off_nunits) : nullptr;
   if (!already_packed) {
-    AGB_CUDA(cudaMemsetAsync(Wh, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
+    // Wh and pn are neighbours in the workspace: one memset for both (unused word rows must read as zero)
+    AGB_CUDA(cudaMemsetAsync(Wh, 0, (pl.off_pn - pl.off_Wh) + (size_t)pl.nt_max * kTileN * 4, st));
     if (Wl) AGB_CUDA(cudaMemsetAsync(Wl, 0, (size_t)pl.nt_max * kTileN * kD * 2, st));
-    AGB_CUDA(cudaMemsetAsync(pn, 0, (size_t)pl.nt_max * kTileN * 4, st));
     tile_pack_kernel<<<1, 256, 0, st>>>(cap_lens, Bc, T, pl.split ? 64 : kTileN, cap_row, tfirst, tncap, ntiles, tcpre,
                                         ufirst, uncap, nunits);
     if (int rc = check_launch("tile_pack_kernel")) return rc;

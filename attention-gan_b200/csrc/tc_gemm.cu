@@ -66,7 +66,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int total = g.nsrc * per_src;
   if (total == 0 && g.accumulate) return;              // empty reduction added to C: nothing to do
   const int stages = g.stages;
-  const int stage_bytes = MT * kChunkBytes16 + NT * 128;
+  const int nt_boxes = (NT + 63) >> 6;                 // B is staged in whole 64-column boxes (NT = 160: 2.5 -> 3)
+  const int stage_bytes = MT * kChunkBytes16 + nt_boxes * 64 * 128;
   const uint32_t tmem_cols = MT * NT <= 128 ? 128u : (MT * NT <= 256 ? 256u : 512u);
 
   if (threadIdx.x == 0) {
@@ -114,7 +115,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (!g.b_mn) {
           tma_load_2d(sb, mB, &full[s], bcol + k0, brow + n0);                    // [NT n][64 k]
         } else {
-          for (int nb = 0; nb < NT / 64; ++nb)
+          for (int nb = 0; nb < nt_boxes; ++nb)
             tma_load_2d(sb + nb * 8192, mB, &full[s], bcol + n0 + nb * 64, brow + k0);
         }
       }
@@ -239,7 +240,11 @@ int tc_gemm2(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap&
   TcGemmArgs g = g_in;
   if (g.M <= 0 || g.N <= 0 || batch <= 0) return 0;
   if (g.K <= 0 || g.K % 64 || g.KB <= 0) return fail_arg("tc_gemm: K=%d must be a positive multiple of 64", g.K);
-  if (g.NT != 64 && g.NT != 128 && g.NT != 192 && g.NT != 256) return fail_arg("tc_gemm: NT=%d", g.NT);
+  // NT = 160 (MN-major B only): two equal column tiles for N = 289...320, so that the CTAs sharing an A operand run
+  // in lockstep and the second read of A hits the L2 (a 192 + 128 split drifts apart: 24 GB instead of 17 GB of DRAM
+  // reads per d img launch, profiles/r2_ncu_attention_and_gemm_metrics.txt)
+  if (g.NT != 64 && g.NT != 128 && g.NT != 192 && g.NT != 256 && !(g.NT == 160 && g.b_mn))
+    return fail_arg("tc_gemm: NT=%d", g.NT);
   if (g.NT0 && (g.NT0 % 64 || g.NT0 > 256 || !g.b_mn)) return fail_arg("tc_gemm: NT0=%d", g.NT0);
   if (g.MT != 1 && g.MT != 2) g.MT = 1;
   const int nt_max = std::max(g.NT, g.NT0);
@@ -258,7 +263,7 @@ int tc_gemm2(const TcGemmArgs& g_in, const CUtensorMap& mapA, const CUtensorMap&
   if (grid.y > 65535 || grid.z > 65535) return fail_unsupported("tc_gemm grid too large");
   // ring depth: as deep as ~192 KB allows; short reductions get a short ring so that several CTAs
   // share an SM and hide each other's prologue
-  const int stage_bytes = g.MT * kChunkBytes16 + nt_max * 128;
+  const int stage_bytes = g.MT * kChunkBytes16 + (nt_max + 63) / 64 * 64 * 128;
   const long long chunks = (long long)g.nsrc * g.KB * (g.K / 64);
   const int max_stages = std::min(kGemmStages, (kGemmSmem - 1024) / stage_bytes);
   g.stages = (int)std::min<long long>(max_stages, std::max<long long>(2, chunks));
@@ -282,12 +287,12 @@ using namespace agb;
 
 // Test hook: C[M,N] = A * B^T for one batch.  A is [M,K] row-major (a_mn = 0) or [K,M] (a_mn = 1);
 // B likewise with N.  M, N arbitrary (<= one grid), K % 64 == 0.  `accumulate`: bit 0 = add to C; bits 8-15 /
-// 16-23 / 24-31 select the tiling under test: NT / 64 (0 = default), NT0 / 64, MT.
+// 16-23 / 24-31 select the tiling under test: NT / 32 (0 = default), NT0 / 64, MT.
 extern "C" int agb_tc_gemm_test(const void* A, const void* B, float* C, int M, int N, int K, int a_mn, int b_mn,
                                 int bf16, int accumulate, void* stream) {
   if (!A || !B || !C) return fail_arg("null pointer");
   CUtensorMap mapA, mapB;
-  const int nt_sel = ((accumulate >> 8) & 0xff) * 64, nt0_sel = ((accumulate >> 16) & 0xff) * 64;
+  const int nt_sel = ((accumulate >> 8) & 0xff) * 32, nt0_sel = ((accumulate >> 16) & 0xff) * 64;
   const int mt_sel = (accumulate >> 24) & 0xff;
   accumulate &= 1;
   const int NT = nt_sel ? nt_sel : ((N % 128 == 0 || N > 64) ? 128 : 64);

@@ -56,7 +56,8 @@ def test_tc_gemm_all_majors(agb, a_mn, b_mn, M, N, K, bf16):
 
 
 @pytest.mark.parametrize("a_mn,b_mn,NT,NT0,MT", [(0, 0, 256, 0, 2), (1, 0, 256, 0, 2), (1, 1, 128, 192, 2),
-                                                 (0, 1, 128, 192, 1), (1, 1, 192, 0, 2), (0, 0, 256, 0, 1)])
+                                                 (0, 1, 128, 192, 1), (1, 1, 192, 0, 2), (0, 0, 256, 0, 1),
+                                                 (1, 1, 160, 0, 2), (0, 1, 160, 0, 1)])
 @pytest.mark.parametrize("M,N,K", [(256, 296, 256), (296, 256, 192), (136, 520, 128)])
 def test_tc_gemm_wide_tiles(agb, a_mn, b_mn, NT, NT0, MT, M, N, K):
     """the wide tilings of the DAMSM reductions: 256-column tiles (d words), a 192 + 128 column split (d img)"""
@@ -69,7 +70,7 @@ def test_tc_gemm_wide_tiles(agb, a_mn, b_mn, NT, NT0, MT, M, N, K):
     C = C0.clone().cuda()
     lib = agb.native.lib()
     st = torch.cuda.current_stream().cuda_stream
-    sel = 1 | ((NT // 64) << 8) | ((NT0 // 64) << 16) | (MT << 24)
+    sel = 1 | ((NT // 32) << 8) | ((NT0 // 64) << 16) | (MT << 24)
     agb.native.check(lib.agb_tc_gemm_test(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, a_mn, b_mn, 0, sel, st),
                      "agb_tc_gemm_test")
     torch.cuda.synchronize()

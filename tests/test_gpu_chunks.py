@@ -189,3 +189,45 @@ def test_f16_loss_within_1e4_of_fp32_path_at_large_batch(agb, B):
     assert _rel(res["f16"][2], res["fp32"][2]) < 5e-3
     assert _rel(res["f16"][3], res["fp32"][3]) < 5e-3
     assert _rel(res["f16"][4], res["fp32"][4]) < 1e-4 and _rel(res["f16"][5], res["fp32"][5]) < 1e-4
+
+
+def test_cfg4_full_size_properties(agb):
+    """BASELINE configs[3] at its FULL size on one GPU (2048 x 2048 pairs, several staging chunks), through
+    size-independent properties: the similarity matrix equals the one assembled from eight 256-image row blocks (what
+    eight ranks compute) bit for bit; the loss from either is the same; padded word slots get exactly zero gradient;
+    every gradient is finite; a row block's image gradient equals the full run's rows when fed the same dLoss/dm."""
+    from attention_gan_b200.agb_native import native, ops
+    B = 2048
+    g = torch.Generator().manual_seed(0)
+    img3 = torch.randn(B, 256, 289, generator=g).cuda()
+    wd = torch.randn(B, 18, 256, generator=g).cuda().transpose(1, 2)
+    lens = torch.randint(2, 19, (B,), generator=g)
+    lens[0] = 18
+    l32 = lens.cuda().to(torch.int32)
+    cls = torch.randint(0, 500, (B,), generator=g).to(torch.int32).cuda()
+    labels = torch.arange(B, device="cuda")
+    mode = native.AGB_MATH_TC_F16
+    m, _, _, ws = ops.damsm_fwd(img3, wd, l32, 4.0, 5.0, 1e-8, 0, False, mode, keep_ws=True, save=True)
+    loss, dm = ops.contrastive(m, cls, labels, 10.0, 5.0, 0, B)
+    dimg, dwords = ops.damsm_bwd(img3, wd, l32, 4.0, 5.0, 1e-8, dm, None, True, mode, m, ws, True)
+    del ws
+    assert torch.isfinite(loss).all() and torch.isfinite(dimg).all() and torch.isfinite(dwords).all()
+    assert 5.0 * 2 * np.log(B) * 0.5 < loss.item() < 5.0 * 2 * np.log(B) * 1.5          # random features: ~ 2 lambda log B
+    pad = torch.arange(18, device="cuda")[None, :] >= l32[:, None]                       # [B, T] padded slots
+    assert (dwords[pad] == 0).all() and (dwords[~pad].abs().sum(1) > 0).all()
+    # eight row blocks of 256 images (one rank's share each)
+    blocks = []
+    for k in range(8):
+        mk, _, _ = ops.damsm_fwd(img3[256 * k:256 * k + 256].contiguous(), wd, l32, 4.0, 5.0, 1e-8, 256 * k, False, mode)
+        blocks.append(mk)
+    m8 = torch.cat(blocks, 0)
+    assert torch.equal(m8, m)
+    loss8, _ = ops.contrastive(m8, cls, labels, 10.0, 5.0, 0, B)
+    assert loss8.item() == loss.item()
+    k = 3
+    sl = slice(256 * k, 256 * k + 256)
+    mk, _, _, wsk = ops.damsm_fwd(img3[sl].contiguous(), wd, l32, 4.0, 5.0, 1e-8, 256 * k, False, mode, keep_ws=True, save=True)
+    dimg_k, _ = ops.damsm_bwd(img3[sl].contiguous(), wd, l32, 4.0, 5.0, 1e-8, dm[sl].contiguous(), None, False, mode, mk, wsk, True)
+    # same arithmetic per (image, word tile); only the fp16 gradient scale (a power of two chosen from the block
+    # height) and the chunking of the word-row reduction differ
+    assert _rel(dimg_k, dimg[sl]) < 2e-3

@@ -822,9 +822,18 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
             // two-CTAs-per-SM variant spills MORE than the straight version: measured with -Xptxas -v).  The packed results of chunk c land on columns that hold only consumed values:
             // ds hi / lo over S (already in registers), a over the first half of G (chunk c covers G columns
             // [16c, 16c+16), a of chunk c goes to [8c, 8c+8)).
+            // The G chunks are double-buffered in registers: the load of chunk c+1 is issued before chunk c is
+            // processed (and the first one before the exponentials), so one TMEM round trip per pass is exposed
+            // instead of one per chunk.
             float s[TL];
             tmem_ld_cols<TL>(tmem + lane0 + u * UB, s);
             tmem_ld_wait();
+            constexpr int kNch = (TL + 15) / 16;
+            float gbuf[2][16];
+            auto load_g = [&](float* g, int c0) {
+              if (TL - c0 >= 16) tmem_ld16(tmem + lane0 + u * UB + NT + c0, g); else tmem_ld8(tmem + lane0 + u * UB + NT + c0, g);
+            };
+            load_g(gbuf[0], 0);
             float mx = fmaxf(s[0], s[1]);
 #pragma unroll
             for (int t = 2; t < TL; t += 2) mx = fmaxf(mx, fmaxf(s[t], s[t + 1]));
@@ -838,13 +847,13 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
             const int pix = (sg.tile0 + j) * 128 + q * 32 + lane;
             float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c0 = 0; c0 < TL; c0 += 16) {
-              constexpr int kW = 16;
-              float g[kW];
-              if (TL - c0 >= 16) tmem_ld16(tmem + lane0 + u * UB + NT + c0, g); else tmem_ld8(tmem + lane0 + u * UB + NT + c0, g);
+            for (int c = 0; c < kNch; ++c) {
+              const int c0 = c * 16;
+              float* g = gbuf[c & 1];
               tmem_ld_wait();
+              load_g(gbuf[(c + 1) & 1], c + 1 < kNch ? c0 + 16 : 0);      // next chunk, or chunk 0 again for the ds pass
 #pragma unroll
-              for (int t = 0; t < kW; ++t) {
+              for (int t = 0; t < 16; ++t) {
                 if (c0 + t < TL) {
                   if (dattn != nullptr && c0 + t < p.T && pix < p.HW) g[t] += to_f32(dattn[(size_t)(c0 + t) * p.HW + pix]);
                   s[c0 + t] *= inv;
@@ -854,12 +863,13 @@ word_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_c
             }
             const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
-            for (int c0 = 0; c0 < NT; c0 += 16) {
+            for (int c = 0; c < NT / 16; ++c) {
+              const int c0 = c * 16;
               uint32_t hi[8], lo[8], pa[8];
               if (c0 < TL) {
-                float g[16];
-                if (TL - c0 >= 16) tmem_ld16(tmem + lane0 + u * UB + NT + c0, g); else tmem_ld8(tmem + lane0 + u * UB + NT + c0, g);
+                float* g = gbuf[(kNch + c) & 1];
                 tmem_ld_wait();
+                if (c + 1 < kNch) load_g(gbuf[(kNch + c + 1) & 1], c0 + 16);
 #pragma unroll
                 for (int t = 0; t < 16; t += 2) {
                   if (c0 + t < TL) {

@@ -231,3 +231,26 @@ def test_cfg4_full_size_properties(agb):
     # same arithmetic per (image, word tile); only the fp16 gradient scale (a power of two chosen from the block
     # height) and the chunking of the word-row reduction differ
     assert _rel(dimg_k, dimg[sl]) < 2e-3
+
+
+@pytest.mark.parametrize("Bg", [48, 2048])
+def test_benchmarked_mode_meets_the_loss_tolerance_on_the_benchmarked_inputs(agb, Bg):
+    """bench.py times math="f16" on its own synthetic batches (cfg2: 48, cfg4: 2048).  north_star's bound on the loss
+    is 1e-4 relative: checked here on EXACTLY those inputs against the split-precision path (fp32-accurate: 1e-5 of
+    the fp64 oracle, tests/test_gpu_tc.py) and, at 48, against the fp64 oracle itself."""
+    import bench
+    img, wrd, cnn, rnn, lens, cls = bench.damsm_inputs(Bg)
+    labels = torch.arange(Bg, device="cuda")
+    out = {}
+    for math in ("f16", "f16x2"):
+        wl, sl, _ = agb.DAMSMLoss("cuda", math=math, att_maps=None).get_losses(
+            img.cuda(), cnn.cuda(), wrd.cuda().transpose(1, 2), rnn.cuda(), labels, lens.cuda(),
+            cls.to(torch.int32).cuda())
+        out[math] = (wl.item(), sl.item())
+        torch.cuda.empty_cache()
+    assert abs(out["f16"][0] - out["f16x2"][0]) <= 1e-4 * abs(out["f16x2"][0]), out
+    assert abs(out["f16"][1] - out["f16x2"][1]) <= 1e-5 * abs(out["f16x2"][1]), out
+    if Bg <= 48:
+        wl0, _, _, _ = cf.words_loss_fwd_bwd(img.numpy().reshape(Bg, 256, -1), wrd.transpose(1, 2).numpy(),
+                                             np.arange(Bg), lens.numpy(), cls.numpy())
+        assert abs(out["f16"][0] - wl0) <= 1e-4 * abs(wl0) and abs(out["f16x2"][0] - wl0) <= 1e-5 * abs(wl0)
